@@ -1,0 +1,118 @@
+/*
+ * C-ABI of the B200-native trajectory_generator hot path.
+ *
+ * One shared library, libTrajectoryConstraints.so, exports
+ *   (A) the reference's own 24 extern "C" symbols, so that it can be dropped at the
+ *       path the reference's ctypes wrappers load
+ *       (CF/TrajectoryConstraintsCCode/build/src/libTrajectoryConstraints.so;
+ *        CF = trajectory_generation/constraint_functions), and
+ *   (B) batched entry points for the whole inner loop of
+ *       TrajectoryGenerator.generate_trajectory (TG/trajectory_generator.py:65-97):
+ *       objective + constraints + analytic Jacobians (what scipy SLSQP calls each
+ *       iteration) and the SLSQP iteration itself, one warp per problem.
+ *
+ * Everything runs on the current CUDA device; there is no CPU fallback: every entry
+ * point returns a non-zero status (and tg_last_error() a message) if no device /
+ * kernel image is available.
+ *
+ * Conventions (same as the reference, CC/src/CBindHelperFunctions.cpp:11-31):
+ * control points are row-major D x N float64.  Batched arrays are row-major with the
+ * problem index slowest.  `spec` is a host array of tg_spec_count() ints (see
+ * trajectory_generator_b200/csrc/tg_spec.h) describing the shape shared by all
+ * problems of a batch; `par` holds one parameter row of layout.P doubles per problem.
+ */
+#ifndef TRAJECTORY_GENERATOR_B200_H
+#define TRAJECTORY_GENERATOR_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------ (B) batched API */
+
+/* number of ints in a spec / in the layout struct */
+int tg_spec_count(void);
+/* fills out[] with struct TgLayout (all ints, field order of tg_spec.h); returns its length */
+int tg_layout(const int *spec, int *out, int cap);
+/* message of the last failing call on this thread ("" if none) */
+const char *tg_last_error(void);
+/* 0 when a CUDA device with an sm_100a image is usable, else an error code */
+int tg_device_check(void);
+
+/*
+ * M1: one evaluation of everything scipy SLSQP asks of the reference's closures:
+ *   f[B], g[B*n] = objective and gradient           (TG/objectives/objective_functions.py:6-62)
+ *   c[B*m]       = constraint rows in SLSQP order   (scipy/optimize/_constraints.py:506-601)
+ *   jnl[B*m_nl*n]= Jacobian rows of the nonlinear rows (dense, row-major)
+ * replaces per problem: 1 + (n+1) calls of the objective and of every constraint closure
+ * (TG/trajectory_generator.py:171-250; scipy 2-point finite differences).
+ * Device pointers; any output pointer may be NULL.  `stream` is a cudaStream_t (NULL = default).
+ */
+int tg_eval_batch(const int *spec, int B, const double *par, const double *x,
+                  double *f, double *g, double *c, double *jnl, void *stream);
+
+/* constant Jacobian of the linear rows, all m rows x n (nonlinear rows left untouched): alin[B*m*n] */
+int tg_linear_rows_batch(const int *spec, int B, const double *par, double *alin, void *stream);
+
+/* flags for tg_solve_batch */
+#define TG_SOLVE_FD_JACOBIAN 1   /* emulate scipy's forward differences (h = 1.4901161193847656e-08) */
+
+/* bytes of device scratch tg_solve_batch needs for this shape (0 if it all fits in shared memory) */
+size_t tg_solve_workspace_bytes(const int *spec, int B);
+
+/*
+ * M2: the per-problem scipy.optimize.minimize(method='SLSQP', options={'disp': False})
+ * call of TG/trajectory_generator.py:87-94, batched.  x[B*n]: in = initial variables
+ * (TG/objectives/objective_variables.py:27-48), out = optimised variables.
+ * status[B] = SLSQP exit mode (0 ok, 4/6 subproblem failures, 8, 9), nit[B] = major iterations,
+ * violation[B] = the reference's is_violation flag (TG/trajectory_generator.py:252-261),
+ * f[B] = final objective.  Device pointers.
+ */
+int tg_solve_batch(const int *spec, int B, const double *par, double *x, double *f,
+                   int *status, int *nit, int *violation, int maxiter, double ftol, int flags,
+                   void *workspace, size_t workspace_bytes, void *stream);
+
+/* host-buffer variants: copy in, launch, copy out (the reference-facing call measured as `e2e`) */
+int tg_eval_host(const int *spec, int B, const double *par, const double *x,
+                 double *f, double *g, double *c, double *jnl);
+int tg_solve_host(const int *spec, int B, const double *par, double *x, double *f,
+                  int *status, int *nit, int *violation, int maxiter, double ftol, int flags);
+
+/* number of kernel launches issued by this library since load (all entry points) */
+unsigned long long tg_launch_count(void);
+
+/* ------------------------------------------------------------------ (A) legacy symbols
+ * Signatures of CC/include/CrossTermBounds.hpp:45-72, CC/include/ObstacleConstraints.hpp:25-49,
+ * CC/include/DerivativeBounds.hpp:63-70 and CC/include/ControlPointDerivativeBounds.hpp:26-33
+ * (CC = CF/TrajectoryConstraintsCCode).  Host pointers; each call is one single-problem
+ * kernel launch.  Returned double* buffers stay valid until the next call on the same
+ * handle (the reference leaks them; scipy copies immediately). */
+#define TG_DECLARE_LEGACY(D)                                                                                     \
+    void *CrossTermBounds_##D(void);                                                                             \
+    double get_spline_curvature_bound_##D(void *obj, double cont_pts[], int num_control_points);                 \
+    double get_spline_angular_rate_bound_##D(void *obj, double cont_pts[], int num_control_points,               \
+                                             double scale_factor);                                               \
+    double get_spline_centripetal_acceleration_bound_##D(void *obj, double cont_pts[], int num_control_points,   \
+                                                         double scale_factor);                                   \
+    void *DerivativeBounds_##D(void);                                                                            \
+    double find_min_velocity_of_spline_##D(void *obj, double cont_pts[], int num_control_points,                 \
+                                           double scale_factor);                                                 \
+    void *ObstacleConstraints_##D(void);                                                                         \
+    double *getObstaclesConstraintsForSpline_##D(void *obj, double obstacle_centers[], double obstacle_radii[],  \
+                                                 int num_obstacles, double cont_pts[], int num_cont_points);     \
+    double *getObstacleConstraintsForIntervals_##D(void *obj, double cont_pts[], int num_cont_points,            \
+                                                   double obstacle_radius, double obstacle_center[]);            \
+    double getObstacleConstraintForSpline_##D(void *obj, double cont_pts[], int num_cont_points,                 \
+                                              double obstacle_radius, double obstacle_center[]);                 \
+    void *ControlPointDerivativeBounds_##D(void);                                                                \
+    double find_min_velocity_of_bez_vel_cont_pts_##D(void *obj, double cont_pts[], int num_control_points);
+
+TG_DECLARE_LEGACY(2)
+TG_DECLARE_LEGACY(3)
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TRAJECTORY_GENERATOR_B200_H */

@@ -1,0 +1,52 @@
+// TEST INFRASTRUCTURE -- single-lane host build of the device headers
+// (csrc/tg_eval.h, csrc/tg_sqp.h) so that the evaluation maths and the SQP
+// logic can be unit-tested in the GPU-less build container against the oracle
+// and scipy.  Never loaded by the product: the product path is the CUDA
+// library built from csrc/tg_api.cu and fails loudly without it.
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+#include "../../trajectory_generator_b200/csrc/tg_eval.h"
+#ifdef TG_WITH_SQP
+#include "../../trajectory_generator_b200/csrc/tg_sqp.h"
+#endif
+
+extern "C" int hs_layout(const int *spec, int *out, int cap)
+{
+    TgLayout L;
+    tg_make_layout(spec, &L);
+    const int cnt = (int)(sizeof(TgLayout) / sizeof(int));
+    if (out && cap >= cnt) memcpy(out, &L, sizeof(TgLayout));
+    return cnt;
+}
+
+// f, g[n], c[m], J[m*n] row-major (all rows, linear ones included)
+extern "C" void hs_eval(const int *spec, const double *par, const double *x, double *f, double *g, double *c, double *J)
+{
+    TgLayout L;
+    tg_make_layout(spec, &L);
+    std::vector<double> scratch(tg_scratch_doubles(L));
+    *f = tg_objective(L, spec, x, g);
+    TgJac sink = {J, L.n, 1, 0};
+    if (J) {
+        tg_linear_jacobian(L, spec, par, sink);
+        tg_constraints(L, spec, par, x, c, &sink, scratch.data());
+    } else {
+        tg_constraints(L, spec, par, x, c, nullptr, scratch.data());
+    }
+}
+
+#ifdef TG_WITH_SQP
+extern "C" int hs_solve(const int *spec, const double *par, double *x, int maxiter, double ftol, int flags, double *fout,
+                        int *status, int *nit, int *nfev, double *trace, int trace_cap)
+{
+    TgLayout L;
+    tg_make_layout(spec, &L);
+    size_t nd = tg_sqp_workspace_doubles(L);
+    std::vector<double> ws(nd);
+    TgSqpResult res;
+    tg_sqp_solve(L, spec, par, x, ws.data(), maxiter, ftol, flags, &res, trace, trace_cap);
+    *fout = res.f; *status = res.status; *nit = res.nit; *nfev = res.nfev;
+    return res.status;
+}
+#endif

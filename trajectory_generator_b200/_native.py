@@ -1,0 +1,100 @@
+"""ctypes binding of the CUDA library (include/trajectory_generator_b200.h).
+
+The library is built in-tree by ``build_native()`` (also called from ``__graft_entry__.build``):
+``trajectory_generator_b200/lib/libTrajectoryConstraints.so`` -- the same file name the
+reference's ctypes wrappers load (CF/turning_constraints.py:12-15), because it also exports the
+reference's 24 legacy symbols.  There is no CPU fallback: if the library is missing, importing
+any compute entry point raises.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib", "libTrajectoryConstraints.so")
+CSRC = os.path.join(HERE, "csrc")
+
+# field order of struct TgLayout (csrc/tg_spec.h)
+LAYOUT_FIELDS = ("d N nint n ia is0 is1 it0 nws niw meq mineq m r_start n_start r_end n_end r_sder n_sder "
+                 "r_eder n_eder r_iwl n_iwl r_iwv n_iwv r_db n_db r_tanl r_tanu n_tan r_turn n_turn r_sfcl r_sfcu "
+                 "n_sfc r_obs n_obs m_nl m_lin turn_first turn_ncp p_start_loc p_end_loc p_target_vel p_sdir p_svel "
+                 "p_sacc p_edir p_evel p_eacc p_iwl p_iwv p_minv p_maxv p_up p_horiz p_maxa p_grav p_jerk p_tanmin "
+                 "p_tanmax p_turn p_sfc p_obs_c p_obs_r P").split()
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-shared"]
+
+
+def build_native(force=False, verbose=False):
+    """Compile csrc/tg_api.cu for sm_100a into lib/libTrajectoryConstraints.so (nvcc cross-compiles without a GPU)."""
+    srcs = [os.path.join(CSRC, f) for f in ("tg_api.cu", "tg_sqp.h", "tg_eval.h", "tg_spec.h")]
+    srcs.append(os.path.join(os.path.dirname(HERE), "include", "trajectory_generator_b200.h"))
+    if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(s) for s in srcs):
+        return LIB_PATH
+    os.makedirs(os.path.dirname(LIB_PATH), exist_ok=True)
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH, srcs[0]]
+    proc = subprocess.run(cmd, capture_output=True, text=True)
+    if proc.returncode != 0:
+        raise RuntimeError("nvcc failed:\n%s\n%s" % (" ".join(cmd), proc.stderr))
+    if verbose:
+        print(proc.stderr)
+    return LIB_PATH
+
+
+_LIB = None
+_F64 = ctypes.POINTER(ctypes.c_double)
+_I32 = ctypes.POINTER(ctypes.c_int)
+
+
+def lib():
+    """The loaded CUDA library; raises if it has not been built (no fallback)."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError("CUDA library %s is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                               "(there is no CPU fallback)" % LIB_PATH)
+        L = ctypes.CDLL(LIB_PATH)
+        L.tg_spec_count.restype = ctypes.c_int
+        L.tg_layout.argtypes = [_I32, _I32, ctypes.c_int]
+        L.tg_layout.restype = ctypes.c_int
+        L.tg_last_error.restype = ctypes.c_char_p
+        L.tg_device_check.restype = ctypes.c_int
+        L.tg_launch_count.restype = ctypes.c_ulonglong
+        vp, sz = ctypes.c_void_p, ctypes.c_size_t
+        L.tg_eval_batch.argtypes = [_I32, ctypes.c_int, vp, vp, vp, vp, vp, vp, vp]
+        L.tg_linear_rows_batch.argtypes = [_I32, ctypes.c_int, vp, vp, vp]
+        L.tg_solve_workspace_bytes.argtypes = [_I32, ctypes.c_int]
+        L.tg_solve_workspace_bytes.restype = sz
+        L.tg_solve_batch.argtypes = [_I32, ctypes.c_int, vp, vp, vp, vp, vp, vp, ctypes.c_int, ctypes.c_double,
+                                     ctypes.c_int, vp, sz, vp]
+        L.tg_eval_host.argtypes = [_I32, ctypes.c_int, vp, vp, vp, vp, vp, vp]
+        L.tg_solve_host.argtypes = [_I32, ctypes.c_int, vp, vp, vp, vp, vp, vp, ctypes.c_int, ctypes.c_double,
+                                    ctypes.c_int]
+        for name in ("tg_eval_batch", "tg_linear_rows_batch", "tg_solve_batch", "tg_eval_host", "tg_solve_host"):
+            getattr(L, name).restype = ctypes.c_int
+        _LIB = L
+    return _LIB
+
+
+def check(rc, what):
+    if rc != 0:
+        raise RuntimeError("%s failed (code %d): %s" % (what, rc, lib().tg_last_error().decode()))
+
+
+def spec_ptr(spec):
+    spec = np.ascontiguousarray(spec, dtype=np.int32)
+    if spec.size != lib().tg_spec_count():
+        raise ValueError("spec must have %d entries" % lib().tg_spec_count())
+    return spec, spec.ctypes.data_as(_I32)
+
+
+def layout_ints(spec):
+    spec, sp = spec_ptr(spec)
+    out = np.zeros(len(LAYOUT_FIELDS), dtype=np.int32)
+    cnt = lib().tg_layout(sp, out.ctypes.data_as(_I32), out.size)
+    if cnt != len(LAYOUT_FIELDS):
+        raise RuntimeError("TgLayout has %d fields, the Python mirror lists %d" % (cnt, len(LAYOUT_FIELDS)))
+    return out

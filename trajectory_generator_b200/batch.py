@@ -1,0 +1,142 @@
+"""Batched entry points over the CUDA library: device-resident (torch tensors as buffers) and
+host-buffer (numpy, copies inside the C call) variants of
+
+  * ``evaluate``  -- M1: objective, gradient, SLSQP-ordered constraint rows and analytic Jacobian
+    rows of the nonlinear constraints, for B problems of one shape; what the reference computes with
+    1 + (n+1) Python calls of every closure per SLSQP iteration (TG/trajectory_generator.py:171-250
+    under scipy's finite differences);
+  * ``solve``     -- M2: the scipy SLSQP call of TG/trajectory_generator.py:87-94 for B problems.
+
+PyTorch is used only to own device memory and streams.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _native
+from .problem import Layout
+
+JACOBIAN_MODES = {"analytic": 0, "fd": 1}     # "fd": scipy's forward differences emulated on the GPU
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def _ptr(t):
+    return ctypes.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _stream(torch, device):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def evaluate(spec, par, x, want=("f", "g", "c", "jnl"), out=None):
+    """Device-resident M1 evaluation.  par [B,P], x [B,n]: float64 CUDA tensors.  Returns a dict of CUDA tensors."""
+    torch = _torch()
+    lay = Layout(spec)
+    if not (par.is_cuda and x.is_cuda):
+        raise RuntimeError("evaluate() needs CUDA tensors (there is no CPU path); use evaluate_host for numpy input")
+    B = x.shape[0]
+    par = par.contiguous(); x = x.contiguous()
+    assert par.dtype == torch.float64 and x.dtype == torch.float64
+    assert par.shape == (B, lay.P) and x.shape == (B, lay.n)
+    dev = x.device
+    res = out if out is not None else {}
+    shapes = {"f": (B,), "g": (B, lay.n), "c": (B, lay.m), "jnl": (B, lay.m_nl, lay.n)}
+    for k in want:
+        if k not in res:
+            res[k] = torch.empty(shapes[k], dtype=torch.float64, device=dev)
+    spec, sp = _native.spec_ptr(spec)
+    with torch.cuda.device(dev):
+        rc = _native.lib().tg_eval_batch(sp, B, _ptr(par), _ptr(x), _ptr(res.get("f")), _ptr(res.get("g")),
+                                         _ptr(res.get("c")), _ptr(res.get("jnl")), _stream(torch, dev))
+    _native.check(rc, "tg_eval_batch")
+    return res
+
+
+def linear_rows(spec, par):
+    """Constant Jacobian rows of the linear blocks: [B, m, n] CUDA tensor (nonlinear rows are zero)."""
+    torch = _torch()
+    lay = Layout(spec)
+    B = par.shape[0]
+    par = par.contiguous()
+    A = torch.zeros((B, lay.m, lay.n), dtype=torch.float64, device=par.device)
+    spec, sp = _native.spec_ptr(spec)
+    with torch.cuda.device(par.device):
+        rc = _native.lib().tg_linear_rows_batch(sp, B, _ptr(par), _ptr(A), _stream(torch, par.device))
+    _native.check(rc, "tg_linear_rows_batch")
+    return A
+
+
+class SolveBuffers:
+    """Reusable device buffers of one solve shape (outputs + the kernel's scratch)."""
+
+    def __init__(self, spec, B, device):
+        torch = _torch()
+        self.spec, self.sp = _native.spec_ptr(spec)
+        self.B = B
+        self.f = torch.empty(B, dtype=torch.float64, device=device)
+        self.status = torch.empty(B, dtype=torch.int32, device=device)
+        self.nit = torch.empty(B, dtype=torch.int32, device=device)
+        self.violation = torch.empty(B, dtype=torch.int32, device=device)
+        with torch.cuda.device(device):
+            nbytes = _native.lib().tg_solve_workspace_bytes(self.sp, B)
+        if nbytes == 0:
+            raise RuntimeError("tg_solve_workspace_bytes: %s" % _native.lib().tg_last_error().decode())
+        self.ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
+
+
+def solve(spec, par, x, maxiter=100, ftol=1e-6, jacobian="analytic", buffers=None):
+    """Device-resident M2 solve.  x [B,n] is overwritten with the optimised variables.
+    Returns dict(x, f, status, nit, violation) of CUDA tensors."""
+    torch = _torch()
+    lay = Layout(spec)
+    if not (par.is_cuda and x.is_cuda):
+        raise RuntimeError("solve() needs CUDA tensors (there is no CPU path); use solve_host for numpy input")
+    B = x.shape[0]
+    assert par.is_contiguous() and x.is_contiguous()
+    assert par.shape == (B, lay.P) and x.shape == (B, lay.n)
+    dev = x.device
+    buf = buffers if buffers is not None else SolveBuffers(spec, B, dev)
+    with torch.cuda.device(dev):
+        rc = _native.lib().tg_solve_batch(buf.sp, B, _ptr(par), _ptr(x), _ptr(buf.f), _ptr(buf.status), _ptr(buf.nit),
+                                          _ptr(buf.violation), int(maxiter), float(ftol), JACOBIAN_MODES[jacobian],
+                                          _ptr(buf.ws), buf.ws.numel(), _stream(torch, dev))
+    _native.check(rc, "tg_solve_batch")
+    return dict(x=x, f=buf.f, status=buf.status, nit=buf.nit, violation=buf.violation)
+
+
+def _np_ptr(a):
+    return ctypes.c_void_p(0 if a is None else a.ctypes.data)
+
+
+def evaluate_host(spec, par, x, want=("f", "g", "c", "jnl")):
+    """Host-buffer M1 evaluation through tg_eval_host (numpy in, numpy out; copies inside the call)."""
+    lay = Layout(spec)
+    par = np.ascontiguousarray(par, dtype=np.float64).reshape(-1, lay.P)
+    x = np.ascontiguousarray(x, dtype=np.float64).reshape(-1, lay.n)
+    B = x.shape[0]
+    shapes = {"f": (B,), "g": (B, lay.n), "c": (B, lay.m), "jnl": (B, lay.m_nl, lay.n)}
+    res = {k: np.empty(shapes[k]) for k in want}
+    spec, sp = _native.spec_ptr(spec)
+    rc = _native.lib().tg_eval_host(sp, B, _np_ptr(par), _np_ptr(x), _np_ptr(res.get("f")), _np_ptr(res.get("g")),
+                                    _np_ptr(res.get("c")), _np_ptr(res.get("jnl")))
+    _native.check(rc, "tg_eval_host")
+    return res
+
+
+def solve_host(spec, par, x0, maxiter=100, ftol=1e-6, jacobian="analytic"):
+    """Host-buffer M2 solve through tg_solve_host.  Returns dict(x, f, status, nit, violation) of numpy arrays."""
+    lay = Layout(spec)
+    par = np.ascontiguousarray(par, dtype=np.float64).reshape(-1, lay.P)
+    x = np.array(x0, dtype=np.float64).reshape(-1, lay.n)
+    B = x.shape[0]
+    f = np.empty(B); status = np.empty(B, dtype=np.int32); nit = np.empty(B, dtype=np.int32)
+    viol = np.empty(B, dtype=np.int32)
+    spec, sp = _native.spec_ptr(spec)
+    rc = _native.lib().tg_solve_host(sp, B, _np_ptr(par), _np_ptr(x), _np_ptr(f), _np_ptr(status), _np_ptr(nit),
+                                     _np_ptr(viol), int(maxiter), float(ftol), JACOBIAN_MODES[jacobian])
+    _native.check(rc, "tg_solve_host")
+    return dict(x=x, f=f, status=status, nit=nit, violation=viol)

@@ -1,0 +1,652 @@
+// Batched sequential quadratic programming: one warp runs the whole SLSQP
+// iteration of one trajectory problem, replacing the per-problem
+// scipy.optimize.minimize(method='SLSQP') call of the reference
+// (TG/trajectory_generator.py:87-94; behaviour restated in SURVEY.md Appendix B,
+// after D. Kraft, "A software package for sequential quadratic programming",
+// DFVLR-FB 88-28, 1988).
+//
+// The outer iteration keeps SLSQP's semantics -- L1 merit function with the
+// multiplier rule mu <- max(|lambda|, (mu+|lambda|)/2), Armijo-type line search
+// with at most 10 quadratic-interpolation trials and alpha >= 0.1, Powell-damped
+// BFGS applied as two rank-one updates of an LDL^T factorisation, reset of the
+// factor when the merit's directional derivative is not negative (more than 5
+// resets -> exit 8), both convergence tests, augmented subproblem (one slack,
+// penalty 100, x10 up to 5 times) for inconsistent linearisations, bound
+// clipping -- so that iterates follow the reference's on the same problem.
+//
+// The QP subproblem is strictly convex, so its solution and multipliers are
+// unique; instead of SLSQP's LSQ/LSEI/LDP/NNLS chain it is solved with a dual
+// active-set method (Goldfarb & Idnani 1983) that works directly on the
+// maintained factor: J = L^-T D^-1/2, an orthogonal-triangular factor of the
+// active normals (Householder on add, Givens on drop).  Jacobians are analytic
+// (tg_eval.h), not finite differences.
+//
+// Every array lives in one per-problem workspace (shared memory on the device);
+// lanes stride over vector entries / matrix rows.  Host build: one lane.
+#ifndef TG_SQP_H
+#define TG_SQP_H
+
+#include "tg_eval.h"
+
+struct TgSqpResult {
+    int status, nit, nfev;
+    double f;
+};
+
+struct TgSqpWs {
+    int n, n1, m, lda, ldq, nc;      // nc = m + 2*n1 (constraints incl. variable bounds)
+    double *x, *xl, *xu, *g, *s, *x0, *u, *v, *w, *gl;
+    double *c, *mu, *r, *cf;
+    double *A, *Lm, *Dd, *Jq, *R;
+    double *z, *dq, *rq, *np, *uq, *xq, *hw;
+    int *act, *iact;
+    double *scratch;
+};
+
+TG_HD int tg_odd(int v) { return v | 1; }
+
+TG_HD size_t tg_sqp_carve(const TgLayout &L, double *base, TgSqpWs *W)
+{
+    const int n = L.n, n1 = n + 1, m = L.m;
+    size_t o = 0;
+    TgSqpWs w;
+    w.n = n; w.n1 = n1; w.m = m; w.lda = tg_odd(m > 0 ? m : 1); w.ldq = tg_odd(n1); w.nc = m + 2 * n1;
+#define TG_TAKE(field, count) w.field = base ? base + o : 0; o += (size_t)(count)
+    TG_TAKE(x, n1); TG_TAKE(xl, n1); TG_TAKE(xu, n1); TG_TAKE(g, n1); TG_TAKE(s, n1); TG_TAKE(x0, n1);
+    TG_TAKE(u, n1); TG_TAKE(v, n1); TG_TAKE(w, n1); TG_TAKE(gl, n1);
+    TG_TAKE(c, m + 1); TG_TAKE(mu, m + 1); TG_TAKE(r, w.nc + 1); TG_TAKE(cf, m + 1);
+    TG_TAKE(Lm, n * n); TG_TAKE(Dd, n1);
+    TG_TAKE(Jq, w.ldq * n1); TG_TAKE(R, w.ldq * n1);
+    TG_TAKE(z, n1); TG_TAKE(dq, n1); TG_TAKE(rq, n1); TG_TAKE(np, n1); TG_TAKE(uq, n1 + 1); TG_TAKE(xq, n1); TG_TAKE(hw, n1);
+    TG_TAKE(scratch, tg_scratch_doubles(L));
+    double *ints = base ? base + o : 0; o += (size_t)((n1 + 1 + w.nc + 1) / 2 + 1);
+    w.act = (int *)ints; w.iact = w.act + n1 + 1;
+    TG_TAKE(A, w.lda * n1);
+#undef TG_TAKE
+    if (W) *W = w;
+    return o;
+}
+
+TG_HD size_t tg_sqp_workspace_doubles(const TgLayout &L) { return tg_sqp_carve(L, 0, 0); }
+
+TG_HD bool tg_finite(double v) { return v - v == 0; }
+
+// ---------------------------------------------------------------------------
+// LDL^T rank-one update  B <- B + sigma z z^T  (composite-t method of Fletcher &
+// Powell, as used by SLSQP's LDL routine).  Lm: unit lower factor, column i at
+// Lm[i*n + j] (j > i); Dd: diagonal.  z is destroyed; w is scratch.
+// ---------------------------------------------------------------------------
+TG_FN void tg_ldl_update(int n, double sigma, double *z, double *Lm, double *Dd, double *w)
+{
+    const int lane = TG_LANE();
+    if (sigma == 0) return;
+    double t = 1 / sigma;
+    if (sigma < 0) {
+        for (int i = lane; i < n; i += TG_NL) w[i] = z[i];
+        TG_SYNC();
+        for (int i = 0; i < n; i++) {
+            const double vv = w[i];
+            t += vv * vv / Dd[i];
+            for (int j = i + 1 + lane; j < n; j += TG_NL) w[j] -= vv * Lm[i * n + j];
+            TG_SYNC();
+        }
+        if (t >= 0) t = DBL_EPSILON / sigma;
+        if (lane == 0) {
+            for (int i = n - 1; i >= 0; i--) {
+                const double uu = w[i];
+                w[i] = t;
+                t -= uu * uu / Dd[i];
+            }
+        }
+        t = tg_bcast(t, 0);
+        TG_SYNC();
+    }
+    for (int i = 0; i < n; i++) {
+        const double vv = z[i], di = Dd[i];
+        const double delta = vv / di;
+        const double tp = sigma < 0 ? w[i] : t + delta * vv;
+        const double alpha = tp / t;
+        TG_SYNC();
+        if (lane == 0) Dd[i] = alpha * di;
+        if (i == n - 1) break;
+        const double beta = delta / tp;
+        if (alpha > 4) {
+            const double gamma = t / tp;
+            for (int j = i + 1 + lane; j < n; j += TG_NL) {
+                const double uu = Lm[i * n + j];
+                Lm[i * n + j] = gamma * uu + beta * z[j];
+                z[j] -= vv * uu;
+            }
+        } else {
+            for (int j = i + 1 + lane; j < n; j += TG_NL) {
+                z[j] -= vv * Lm[i * n + j];
+                Lm[i * n + j] += beta * z[j];
+            }
+        }
+        t = tp;
+        TG_SYNC();
+    }
+    TG_SYNC();
+}
+
+// out = L D L^T s  (tmp: n scratch)
+TG_FN void tg_ldl_apply(int n, const double *Lm, const double *Dd, const double *s, double *tmp, double *out)
+{
+    const int lane = TG_LANE();
+    for (int i = lane; i < n; i += TG_NL) {
+        double h = s[i];
+        for (int j = i + 1; j < n; j++) h += Lm[i * n + j] * s[j];
+        tmp[i] = Dd[i] * h;
+    }
+    TG_SYNC();
+    for (int i = lane; i < n; i += TG_NL) {
+        double h = tmp[i];
+        for (int j = 0; j < i; j++) h += Lm[j * n + i] * tmp[j];
+        out[i] = h;
+    }
+    TG_SYNC();
+}
+
+// ---------------------------------------------------------------------------
+// QP subproblem:  min 1/2 s'Bs + g's   s.t.  A_eq s + c_eq = 0,  A_in s + c_in >= 0,  u <= s <= v
+// with B = L D L' (dimension n) plus, for the augmented problem (nq = n+1), a
+// last diagonal entry rho.  Non-finite u/v entries mean "no bound".
+// Output: W.xq (step), W.r (multipliers of rows, lower bounds, upper bounds).
+// returns 1 solved (SLSQP's LSQ mode 1), 4 inconsistent constraints, 6 dependent
+// equality normals, 3 iteration limit.
+// ---------------------------------------------------------------------------
+#define TG_QP_OK 1
+
+TG_HD void tg_qp_normal(const TgSqpWs &W, int nq, int p, double *np)
+{
+    const int lane = TG_LANE();
+    if (p < W.m) {
+        for (int i = lane; i < nq; i += TG_NL) np[i] = W.A[i * W.lda + p];
+    } else {
+        const int q = p - W.m;
+        const int i0 = q < W.n1 ? q : q - W.n1;
+        const double sg = q < W.n1 ? 1.0 : -1.0;
+        for (int i = lane; i < nq; i += TG_NL) np[i] = i == i0 ? sg : 0.0;
+    }
+    TG_SYNC();
+}
+
+// value of constraint p at xq (lane-parallel reduction; same result on all lanes)
+TG_HD double tg_qp_value(const TgSqpWs &W, int nq, int p)
+{
+    if (p < W.m) {
+        double s = 0;
+        for (int i = TG_LANE(); i < nq; i += TG_NL) s += W.A[i * W.lda + p] * W.xq[i];
+        return tg_wsum(s) + W.c[p];
+    }
+    const int q = p - W.m;
+    return q < W.n1 ? W.xq[q] - W.u[q] : W.v[q - W.n1] - W.xq[q - W.n1];
+}
+
+// d = J' np ; z = J2 d2 ; rq = R^-1 d1 ; returns |d2|^2 (= z.np) and |d|^2
+TG_FN void tg_qp_directions(const TgSqpWs &W, int nq, int iq, double &d2n, double &dn)
+{
+    const int lane = TG_LANE(), ld = W.ldq;
+    double a = 0, b = 0;
+    for (int k = lane; k < nq; k += TG_NL) {
+        double h = 0;
+        const double *col = W.Jq + k * ld;
+        for (int i = 0; i < nq; i++) h += col[i] * W.np[i];
+        W.dq[k] = h;
+        W.hw[k] = h;
+        if (k >= iq) a += h * h;
+        b += h * h;
+    }
+    d2n = tg_wsum(a);
+    dn = tg_wsum(b);
+    TG_SYNC();
+    for (int i = lane; i < nq; i += TG_NL) {
+        double h = 0;
+        for (int k = iq; k < nq; k++) h += W.Jq[k * ld + i] * W.dq[k];
+        W.z[i] = h;
+    }
+    // back substitution R rq = d1 (column oriented; hw holds the running right-hand side)
+    for (int j = iq - 1; j >= 0; j--) {
+        const double rj = W.hw[j] / W.R[j * ld + j];
+        TG_SYNC();
+        if (lane == 0) W.rq[j] = rj;
+        for (int k = lane; k < j; k += TG_NL) W.hw[k] -= W.R[j * ld + k] * rj;
+        TG_SYNC();
+    }
+    TG_SYNC();
+}
+
+// append constraint with J'np = dq to the factorisation (Householder on dq[iq..])
+TG_FN void tg_qp_add(const TgSqpWs &W, int nq, int iq)
+{
+    const int lane = TG_LANE(), ld = W.ldq;
+    double nn = 0;
+    for (int k = iq + lane; k < nq; k += TG_NL) nn += W.dq[k] * W.dq[k];
+    nn = tg_wsum(nn);
+    const double d0 = W.dq[iq];
+    const double sigma = d0 > 0 ? -sqrt(nn) : sqrt(nn);
+    // w = d2 - sigma e1 ;  w'w = 2 (nn - sigma d0)
+    const double ww = 2 * (nn - sigma * d0);
+    TG_SYNC();
+    if (ww > 0) {
+        for (int i = lane; i < nq; i += TG_NL) {
+            double t = 0;
+            for (int k = iq; k < nq; k++) t += W.Jq[k * ld + i] * (k == iq ? d0 - sigma : W.dq[k]);
+            t *= 2 / ww;
+            for (int k = iq; k < nq; k++) W.Jq[k * ld + i] -= t * (k == iq ? d0 - sigma : W.dq[k]);
+        }
+    }
+    for (int k = lane; k < iq; k += TG_NL) W.R[iq * ld + k] = W.dq[k];
+    if (lane == 0) W.R[iq * ld + iq] = ww > 0 ? sigma : d0;
+    TG_SYNC();
+}
+
+// remove the constraint at position l of the active list
+TG_FN void tg_qp_drop(const TgSqpWs &W, int nq, int &iq, int l)
+{
+    const int lane = TG_LANE(), ld = W.ldq;
+    if (lane == 0) W.iact[W.act[l]] = 0;
+    for (int k = l; k < iq - 1; k++) {
+        for (int i = lane; i <= k + 1; i += TG_NL) W.R[k * ld + i] = W.R[(k + 1) * ld + i];
+        if (lane == 0) { W.act[k] = W.act[k + 1]; W.uq[k] = W.uq[k + 1]; }
+        TG_SYNC();
+    }
+    iq--;
+    for (int j = l; j < iq; j++) {
+        double cc = W.R[j * ld + j], ss = W.R[j * ld + j + 1];
+        const double h = sqrt(cc * cc + ss * ss);
+        TG_SYNC();
+        if (h == 0) continue;
+        cc /= h; ss /= h;
+        if (lane == 0) { W.R[j * ld + j] = h; W.R[j * ld + j + 1] = 0; }
+        for (int k = j + 1 + lane; k < iq; k += TG_NL) {
+            const double t1 = W.R[k * ld + j], t2 = W.R[k * ld + j + 1];
+            W.R[k * ld + j] = cc * t1 + ss * t2;
+            W.R[k * ld + j + 1] = -ss * t1 + cc * t2;
+        }
+        for (int i = lane; i < nq; i += TG_NL) {
+            const double t1 = W.Jq[j * ld + i], t2 = W.Jq[(j + 1) * ld + i];
+            W.Jq[j * ld + i] = cc * t1 + ss * t2;
+            W.Jq[(j + 1) * ld + i] = -ss * t1 + cc * t2;
+        }
+        TG_SYNC();
+    }
+    TG_SYNC();
+}
+
+TG_FN int tg_qp_solve(const TgSqpWs &W, int nq, int meq, double rho)
+{
+    const int lane = TG_LANE(), n = W.n, ld = W.ldq, m = W.m;
+    const int nc = m + 2 * W.n1;
+    const double EPS_DEP = 1e-26;     // |d2|^2 <= EPS_DEP |d|^2 : normal lies in the span of the active ones
+    // ---- J = L^-T D^-1/2 (upper triangular), augmented entry 1/sqrt(rho)
+    for (int k = lane; k < nq; k += TG_NL) {
+        double *col = W.Jq + k * ld;
+        for (int i = 0; i < nq; i++) col[i] = 0;
+        if (k < n) {
+            col[k] = 1;
+            for (int i = k - 1; i >= 0; i--) {
+                double h = 0;
+                for (int j = i + 1; j <= k; j++) h += W.Lm[i * n + j] * col[j];
+                col[i] = -h;
+            }
+            const double sc = 1 / sqrt(W.Dd[k]);
+            for (int i = 0; i <= k; i++) col[i] *= sc;
+        } else col[k] = 1 / rho;      // SLSQP's LSQ puts rho itself (not its root) on the diagonal of E: penalty rho^2/2 delta^2
+    }
+    for (int p = lane; p < nc; p += TG_NL) { W.iact[p] = 0; W.r[p] = 0; }
+    TG_SYNC();
+    // ---- unconstrained minimiser xq = -J J' g
+    for (int k = lane; k < nq; k += TG_NL) {
+        double h = 0;
+        for (int i = 0; i < nq; i++) h += W.Jq[k * ld + i] * W.g[i];
+        W.dq[k] = h;
+    }
+    TG_SYNC();
+    for (int i = lane; i < nq; i += TG_NL) {
+        double h = 0;
+        for (int k = 0; k < nq; k++) h += W.Jq[k * ld + i] * W.dq[k];
+        W.xq[i] = -h;
+    }
+    TG_SYNC();
+    int iq = 0;
+    double d2n, dn;
+    // ---- equality rows, in order
+    for (int p = 0; p < meq; p++) {
+        tg_qp_normal(W, nq, p, W.np);
+        tg_qp_directions(W, nq, iq, d2n, dn);
+        if (!(d2n > EPS_DEP * dn)) return 6;
+        const double sv = tg_qp_value(W, nq, p);
+        const double t2 = -sv / d2n;
+        for (int i = lane; i < nq; i += TG_NL) W.xq[i] += t2 * W.z[i];
+        for (int k = lane; k < iq; k += TG_NL) W.uq[k] -= t2 * W.rq[k];
+        if (lane == 0) { W.uq[iq] = t2; W.act[iq] = p; W.iact[p] = 1; }
+        TG_SYNC();
+        tg_qp_add(W, nq, iq);
+        iq++;
+    }
+    // ---- inequality rows and bounds
+    const int itmax = 10 * (nc + nq) + 100;
+    for (int it = 0; it < itmax; it++) {
+        // most violated inactive constraint
+        double best = 0; int ip = 0x7fffffff;
+        for (int p = meq + lane; p < nc; p += TG_NL) {
+            if (W.iact[p]) continue;
+            double sv, tol;
+            if (p < m) {
+                double h = 0, sc = fabs(W.c[p]);
+                for (int i = 0; i < nq; i++) { const double t = W.A[i * W.lda + p] * W.xq[i]; h += t; sc += fabs(t); }
+                sv = h + W.c[p];
+                tol = 1e-13 * sc;
+            } else {
+                const int q = p - m;
+                const int i = q < W.n1 ? q : q - W.n1;
+                if (i >= nq) continue;
+                const double bnd = q < W.n1 ? W.u[i] : W.v[i];
+                if (!tg_finite(bnd)) continue;
+                sv = q < W.n1 ? W.xq[i] - bnd : bnd - W.xq[i];
+                tol = 1e-13 * (fabs(bnd) + fabs(W.xq[i]));
+            }
+            if (sv < -tol && sv < best) { best = sv; ip = p; }
+        }
+        tg_wargmin(best, ip);
+        if (ip == 0x7fffffff) {
+            for (int k = lane; k < iq; k += TG_NL) W.r[W.act[k]] = W.uq[k];
+            TG_SYNC();
+            return TG_QP_OK;
+        }
+        tg_qp_normal(W, nq, ip, W.np);
+        double uip = 0;
+        double sv = tg_qp_value(W, nq, ip);
+        for (int inner = 0; inner < itmax; inner++) {
+            tg_qp_directions(W, nq, iq, d2n, dn);
+            // dual step length: active inequalities whose multiplier would turn negative
+            double t1 = INFINITY; int l = 0x7fffffff;
+            for (int k = lane; k < iq; k += TG_NL)
+                if (W.act[k] >= meq && W.rq[k] > 0) {
+                    const double t = W.uq[k] / W.rq[k];
+                    if (t < t1) { t1 = t; l = k; }
+                }
+            tg_wargmin(t1, l);
+            const double t2 = d2n > EPS_DEP * dn ? -sv / d2n : INFINITY;
+            const double t = t1 < t2 ? t1 : t2;
+            if (!(t < INFINITY)) return 4;
+            for (int k = lane; k < iq; k += TG_NL) W.uq[k] -= t * W.rq[k];
+            uip += t;
+            if (!(t2 < INFINITY)) {
+                TG_SYNC();
+                tg_qp_drop(W, nq, iq, l);
+                continue;
+            }
+            for (int i = lane; i < nq; i += TG_NL) W.xq[i] += t * W.z[i];
+            TG_SYNC();
+            if (t2 <= t1) {
+                if (lane == 0) { W.uq[iq] = uip; W.act[iq] = ip; W.iact[ip] = 1; }
+                TG_SYNC();
+                tg_qp_add(W, nq, iq);
+                iq++;
+                break;
+            }
+            tg_qp_drop(W, nq, iq, l);
+            sv = tg_qp_value(W, nq, ip);
+            if (inner == itmax - 1) return 3;
+        }
+    }
+    return 3;
+}
+
+// sum of constraint violations / L1 penalty term
+TG_HD double tg_violation(const TgSqpWs &W, int meq, const double *weights)
+{
+    double h = 0;
+    for (int j = TG_LANE(); j < W.m; j += TG_NL) {
+        const double cj = W.c[j];
+        const double viol = j < meq ? fmax(-cj, cj) : fmax(-cj, 0.0);
+        h += weights ? weights[j] * viol : viol;
+    }
+    return tg_wsum(h);
+}
+
+#define TG_SQP_FD_JACOBIAN 1     // flags bit 0: finite-difference emulation instead of analytic derivatives
+#define TG_FD_STEP 1.4901161193847656e-08     // scipy/optimize/_slsqp_py.py:34
+
+// objective and constraints at W.x; with derivs also g and the nonlinear rows of A (analytic)
+TG_FN double tg_sqp_evaluate(const TgLayout &L, const int *sp, const double *par, const TgSqpWs &W, bool derivs)
+{
+    const double f = tg_objective(L, sp, W.x, derivs ? W.g : 0);
+    TgJac sink = {W.A, 1, W.lda, 0};
+    tg_constraints(L, sp, par, W.x, W.c, derivs ? &sink : 0, W.scratch);
+    TG_SYNC();
+    return f;
+}
+
+// Derivatives exactly as the reference obtains them: scipy's approx_derivative('2-point',
+// abs_step=eps, bounds) on the objective and on every nonlinear constraint
+// (scipy/optimize/_slsqp_py.py:353-366, _numdiff.py); linear rows keep their constant A.
+// Requires f, W.c at W.x.  n extra evaluations.
+TG_FN void tg_sqp_fd_derivatives(const TgLayout &L, const int *sp, const double *par, const TgSqpWs &W, double f)
+{
+    const int lane = TG_LANE(), n = L.n, m = L.m;
+    for (int i = 0; i < n; i++) {
+        const double xi = W.x[i], lo = W.xl[i], hi = W.xu[i];
+        double h = TG_FD_STEP;
+        const double xt = xi + h;
+        if (xt < lo || xt > hi) {
+            const double ld = xi - lo, ud = hi - xi;
+            if (fabs(h) <= fmax(ld, ud)) h = -h;
+            else h = ud >= ld ? ud : -ld;
+        }
+        TG_SYNC();
+        if (lane == 0) W.x[i] = xi + h;
+        TG_SYNC();
+        const double dx = W.x[i] - xi;
+        const double f1 = tg_objective(L, sp, W.x, 0);
+        tg_constraints(L, sp, par, W.x, W.cf, 0, W.scratch);
+        TG_SYNC();
+        if (lane == 0) { W.g[i] = (f1 - f) / dx; W.x[i] = xi; }
+        for (int j = lane; j < m; j += TG_NL)
+            if (tg_nlrow(L, j) >= 0) W.A[i * W.lda + j] = (W.cf[j] - W.c[j]) / dx;
+        TG_SYNC();
+    }
+}
+
+// trace (host tests only): per major iteration [f, alpha, x...]
+TG_FN void tg_sqp_solve(const TgLayout &L, const int *sp, const double *par, double *xio, double *wsbase, int maxiter,
+                        double acc, int flags, TgSqpResult *res, double *trace, int trace_cap)
+{
+    TgSqpWs W;
+    tg_sqp_carve(L, wsbase, &W);
+    const int lane = TG_LANE(), n = L.n, m = L.m, meq = L.meq, n1 = W.n1;
+    const double tol = 10 * acc;
+    const bool fd = (flags & TG_SQP_FD_JACOBIAN) != 0;
+    // ---- variables and bounds (TG/objectives/objective_variables.py:50-61); x0 clipped as scipy does
+    for (int i = lane; i < n1; i += TG_NL) {
+        double lo = -INFINITY, hi = INFINITY;
+        if (i >= L.ia && i < L.it0) lo = 10e-8;
+        if (i >= L.it0 && i < n) { lo = 0; hi = L.N - 3; }
+        W.xl[i] = lo; W.xu[i] = hi;
+        double xv = i < n ? xio[i] : 0.0;
+        if (i < n) { xv = xv < lo ? lo : xv; xv = xv > hi ? hi : xv; }
+        W.x[i] = xv; W.s[i] = 0; W.g[i] = 0;
+    }
+    for (int j = lane; j < m; j += TG_NL) W.mu[j] = 0;
+    for (int q = lane; q < W.lda * n1; q += TG_NL) W.A[q] = 0;
+    TG_SYNC();
+    {
+        TgJac sink = {W.A, 1, W.lda, 0};
+        tg_linear_jacobian(L, sp, par, sink);
+    }
+    double f = tg_sqp_evaluate(L, sp, par, W, !fd);
+    if (fd) tg_sqp_fd_derivatives(L, sp, par, W, f);
+    int nfev = 1, iter = 0, ireset = 0, status = -1;
+    double f0 = f, h1, h2, h3, h4, t0, gs;
+    bool badlin = false;
+    bool need_reset = true;
+    for (;;) {
+        if (need_reset) {
+            // ---- reset the BFGS factor to the identity
+            ireset++;
+            if (ireset > 5) {
+                // relaxed convergence test after a positive directional derivative
+                double sn = 0;
+                for (int i = lane; i < n; i += TG_NL) sn += W.s[i] * W.s[i];
+                sn = sqrt(tg_wsum(sn));
+                h3 = tg_violation(W, meq, 0);
+                status = ((fabs(f - f0) < tol || sn < tol) && h3 < tol && !badlin && f == f) ? 0 : 8;
+                break;
+            }
+            for (int q = lane; q < n * n; q += TG_NL) W.Lm[q] = 0;
+            for (int i = lane; i < n1; i += TG_NL) W.Dd[i] = 1;
+            TG_SYNC();
+            need_reset = false;
+        }
+        // ---- major iteration
+        iter++;
+        if (iter > maxiter) { status = 9; break; }
+        for (int i = lane; i < n; i += TG_NL) { W.u[i] = W.xl[i] - W.x[i]; W.v[i] = W.xu[i] - W.x[i]; }
+        TG_SYNC();
+        h4 = 1;
+#ifdef TG_DEBUG_KKT
+        if (getenv("TG_DUMP_ITER") && atoi(getenv("TG_DUMP_ITER")) == iter) {
+            FILE *fp = fopen("/tmp/qp_dump.txt", "w");
+            fprintf(fp, "%d %d %d\n", n, m, meq);
+            for (int i = 0; i < n; i++) fprintf(fp, "%.17g ", W.g[i]); fprintf(fp, "\n");
+            for (int j = 0; j < m; j++) fprintf(fp, "%.17g ", W.c[j]); fprintf(fp, "\n");
+            for (int j = 0; j < m; j++) { for (int i = 0; i < n; i++) fprintf(fp, "%.17g ", W.A[i * W.lda + j]); fprintf(fp, "\n"); }
+            for (int i = 0; i < n; i++) fprintf(fp, "%.17g ", W.u[i]); fprintf(fp, "\n");
+            for (int i = 0; i < n; i++) fprintf(fp, "%.17g ", W.v[i]); fprintf(fp, "\n");
+            for (int i = 0; i < n; i++) fprintf(fp, "%.17g ", W.Dd[i]); fprintf(fp, "\n");
+            for (int i = 0; i < n; i++) { for (int j = 0; j < n; j++) fprintf(fp, "%.17g ", j > i ? W.Lm[i * n + j] : (i == j ? 1.0 : 0.0)); fprintf(fp, "\n"); }
+            fclose(fp);
+        }
+#endif
+        int mode = tg_qp_solve(W, n, meq, 0.0);
+        badlin = false;
+        if (mode == 6 && n == meq) mode = 4;
+        if (mode == 4) {
+            // ---- augmented problem for an inconsistent linearisation
+            badlin = true;
+            for (int j = lane; j < m; j += TG_NL) W.A[n * W.lda + j] = j < meq ? -W.c[j] : fmax(-W.c[j], 0.0);
+            if (lane == 0) { W.g[n] = 0; W.u[n] = 0; W.v[n] = 1; }
+            TG_SYNC();
+            double rho = 100;
+            for (int incons = 0;; incons++) {
+                mode = tg_qp_solve(W, n1, meq, rho);
+                if (mode != 4) break;
+                rho *= 10;
+                if (incons + 1 > 5) break;
+            }
+            if (mode != TG_QP_OK) { status = mode; break; }
+            h4 = 1 - W.xq[n];
+        } else if (mode != TG_QP_OK) { status = mode; break; }
+#ifdef TG_DEBUG_KKT
+        {
+            // host-only diagnostics: KKT residual of the QP solution
+            double v[64]; tg_ldl_apply(n, W.Lm, W.Dd, W.xq, W.w, v);
+            double rs = 0, feas = 0, comp = 0, mneg = 0;
+            for (int i = 0; i < n; i++) {
+                double h = v[i] + W.g[i];
+                for (int j = 0; j < m; j++) h -= W.A[i * W.lda + j] * W.r[j];
+                h -= W.r[m + i]; h += W.r[m + n1 + i];
+                rs = fmax(rs, fabs(h));
+            }
+            for (int j = 0; j < m; j++) {
+                double h = W.c[j];
+                for (int i = 0; i < n; i++) h += W.A[i * W.lda + j] * W.xq[i];
+                if (j < meq) feas = fmax(feas, fabs(h)); else { feas = fmax(feas, -h); comp = fmax(comp, fabs(h * W.r[j])); mneg = fmin(mneg, W.r[j]); }
+            }
+            double dmin = 1e300, dmax = 0; for (int i = 0; i < n; i++) { dmin = fmin(dmin, W.Dd[i]); dmax = fmax(dmax, W.Dd[i]); }
+            double gn = 0, sn_ = 0; for (int i = 0; i < n; i++) { gn = fmax(gn, fabs(W.g[i])); sn_ = fmax(sn_, fabs(W.xq[i])); }
+            printf("  [kkt] iter %d mode %d badlin %d stat %.2e feas %.2e comp %.2e minmult %.2e f %.10g Dmin %.2e Dmax %.2e |g| %.2e |s| %.2e delta %.3g\n", iter, mode, (int)badlin, rs, feas, comp, mneg, f, dmin, dmax, gn, sn_, badlin ? W.xq[n] : 0.0);
+        }
+#endif
+        // ---- gradient of the Lagrangian at the old point, merit weights
+        for (int i = lane; i < n; i += TG_NL) {
+            double h = W.g[i];
+            for (int j = 0; j < m; j++) h -= W.A[i * W.lda + j] * W.r[j];
+            W.gl[i] = h;
+            W.s[i] = W.xq[i];
+            W.x0[i] = W.x[i];
+        }
+        f0 = f;
+        TG_SYNC();
+        gs = 0;
+        for (int i = lane; i < n; i += TG_NL) gs += W.g[i] * W.s[i];
+        gs = tg_wsum(gs);
+        h1 = 0; h2 = 0;
+        for (int j = lane; j < m; j += TG_NL) {
+            const double cj = W.c[j];
+            h2 += fmax(-cj, j < meq ? cj : 0.0);
+            const double ar = fabs(W.r[j]);
+            W.mu[j] = fmax(ar, (W.mu[j] + ar) / 2);
+            h1 += ar * fabs(cj);
+        }
+        h1 = fabs(gs) + tg_wsum(h1);
+        h2 = tg_wsum(h2);
+        TG_SYNC();
+        if (h1 < acc && h2 < acc && !badlin && f == f) { status = 0; break; }
+        h1 = tg_violation(W, meq, W.mu);
+        t0 = f + h1;
+        h3 = gs - h1 * h4;
+        if (h3 >= 0) { need_reset = true; continue; }
+        // ---- line search on the L1 merit function
+        double alpha = 1;
+        for (int line = 1;; line++) {
+            h3 = alpha * h3;
+            for (int i = lane; i < n; i += TG_NL) {
+                W.s[i] *= alpha;
+                double xv = W.x0[i] + W.s[i];
+                xv = xv < W.xl[i] ? W.xl[i] : xv;
+                xv = xv > W.xu[i] ? W.xu[i] : xv;
+                W.x[i] = xv;
+            }
+            TG_SYNC();
+            f = tg_sqp_evaluate(L, sp, par, W, !fd);
+            nfev++;
+            const double t = f + tg_violation(W, meq, W.mu);
+            h1 = t - t0;
+            if (h1 <= h3 / 10 || line > 10) break;
+            alpha = fmax(h3 / (2 * (h3 - h1)), 0.1);
+        }
+        if (trace && lane == 0 && (iter * (n + 2) <= trace_cap)) {
+            double *tr = trace + (iter - 1) * (n + 2);
+            tr[0] = f; tr[1] = alpha;
+            for (int i = 0; i < n; i++) tr[2 + i] = W.x[i];
+        }
+        // ---- convergence test after the step
+        {
+            double sn = 0;
+            for (int i = lane; i < n; i += TG_NL) sn += W.s[i] * W.s[i];
+            sn = sqrt(tg_wsum(sn));
+            h3 = tg_violation(W, meq, 0);
+            if ((fabs(f - f0) < acc || sn < acc) && h3 < acc && !badlin && f == f) { status = 0; break; }
+        }
+        // ---- damped BFGS update of L D L' (analytic derivatives at the new point are already in g, A)
+        if (fd) { tg_sqp_fd_derivatives(L, sp, par, W, f); nfev += n; }
+        for (int i = lane; i < n; i += TG_NL) {
+            double h = W.g[i];
+            for (int j = 0; j < m; j++) h -= W.A[i * W.lda + j] * W.r[j];
+            W.u[i] = h - W.gl[i];
+        }
+        TG_SYNC();
+        tg_ldl_apply(n, W.Lm, W.Dd, W.s, W.w, W.v);
+        h1 = 0; h2 = 0;
+        for (int i = lane; i < n; i += TG_NL) { h1 += W.s[i] * W.u[i]; h2 += W.s[i] * W.v[i]; }
+        h1 = tg_wsum(h1); h2 = tg_wsum(h2);
+        h3 = 0.2 * h2;
+        if (h1 < h3) {
+            h4 = (h2 - h3) / (h2 - h1);
+            h1 = h3;
+            for (int i = lane; i < n; i += TG_NL) W.u[i] = h4 * W.u[i] + (1 - h4) * W.v[i];
+        }
+        TG_SYNC();
+        if (h1 == 0 || h2 == 0) { need_reset = true; continue; }
+        tg_ldl_update(n, 1 / h1, W.u, W.Lm, W.Dd, W.w);
+        tg_ldl_update(n, -1 / h2, W.v, W.Lm, W.Dd, W.w);
+    }
+    for (int i = lane; i < n; i += TG_NL) xio[i] = W.x[i];
+    TG_SYNC();
+    if (res && lane == 0) { res->status = status; res->nit = iter > maxiter ? maxiter : iter; res->nfev = nfev; res->f = f; }
+}
+
+#endif  // TG_SQP_H

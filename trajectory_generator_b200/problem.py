@@ -1,0 +1,218 @@
+"""Host-side problem packing: ``ConstraintsContainer`` -> (shape descriptor, parameter row, x0, bounds).
+
+Mirrors what ``TrajectoryGenerator.generate_trajectory`` assembles before it calls SLSQP
+(reference TG/trajectory_generator.py:65-86, 134-250 and TG/objectives/objective_variables.py:27-105):
+number of intervals / control points, the variable vector ``[P row-major | alpha | direction
+scalars | intermediate times]``, its bounds and initial guess, and which constraint blocks exist.
+The blocks themselves are evaluated on the GPU (csrc/tg_eval.h); here they are reduced to the
+int32 descriptor of csrc/tg_spec.h plus one flat float64 parameter row per problem.
+"""
+import numpy as np
+
+from . import _native
+
+OBJECTIVES = ("minimal_time_path", "minimal_distance_path", "minimal_velocity_path",
+              "minimal_acceleration_path", "minimal_distance_and_time_path",
+              "minimal_velocity_and_time_path", "minimal_acceleration_and_time_path",
+              "minimal_time_path_velocity_penalty")
+TURN_KINDS = {"curvature": 1, "angular_rate": 2, "centripetal_acceleration": 3}
+
+# indices into the spec array: keep in step with enum TgSpecField (csrc/tg_spec.h)
+MAX_CORRIDORS = 8
+(SP_DIM, SP_NCP, SP_OBJECTIVE, SP_START_KIND, SP_END_KIND, SP_START_DIR, SP_START_VEL, SP_START_ACC,
+ SP_END_DIR, SP_END_VEL, SP_END_ACC, SP_NIW, SP_IW_VEL, SP_DB_MINV, SP_DB_MAXV, SP_DB_UP, SP_DB_HORIZ,
+ SP_DB_MAXA, SP_DB_GRAV, SP_DB_JERK, SP_TANG, SP_TURN, SP_NCORR, SP_IPC0) = range(24)
+SP_NOBST = SP_IPC0 + MAX_CORRIDORS
+SP_COUNT = SP_NOBST + 1
+
+VARIABLE_LOWER_BOUND = 10e-8     # TG/objectives/objective_variables.py:56 (the literal is 10e-8 = 1e-7)
+
+
+class Layout:
+    """Row / column / parameter offsets derived from a spec (struct TgLayout of csrc/tg_spec.h)."""
+
+    def __init__(self, spec):
+        for name, value in zip(_native.LAYOUT_FIELDS, _native.layout_ints(spec)):
+            setattr(self, name, int(value))
+
+
+class PackedProblem:
+    def __init__(self, spec, par, x0, xl, xu):
+        self.spec, self.par, self.x0, self.xl, self.xu = spec, par, x0, xl, xu
+        self.layout = Layout(spec)
+
+    @property
+    def key(self):
+        return self.spec.tobytes()
+
+
+def _flat(a):
+    return np.asarray(a, dtype=np.float64).flatten()
+
+
+def num_intervals_free_space(waypoint_data, requested=None):
+    """TG/trajectory_generator.py:134-146."""
+    if requested is not None:
+        return requested
+    s0 = waypoint_data.start_waypoint.checkIfZeroVel()
+    s1 = waypoint_data.end_waypoint.checkIfZeroVel()
+    return 5 + 2 * int(s0) + 2 * int(s1) + int(s0 and s1)
+
+
+def initial_control_points(num_cont_pts, point_sequence, dimension):
+    """Straight line, or equal arc-length steps along the polyline (TG/objectives/objective_variables.py:63-93)."""
+    seq = np.asarray(point_sequence, dtype=np.float64)
+    nseg = seq.shape[1] - 1
+    if nseg < 2:
+        return np.linspace(seq[:, 0], seq[:, 1], num_cont_pts).T
+    cps = np.empty((dimension, num_cont_pts))
+    cum = np.cumsum(np.linalg.norm(seq[:, 1:] - seq[:, :-1], 2, 0))
+    spacing = cum[nseg - 1] / (num_cont_pts - 1)
+    seg, walked, anchor, step = 0, 0.0, seq[:, 0], 0.0
+    for i in range(num_cont_pts - 1):
+        heading = seq[:, seg + 1] - seq[:, seg]
+        cps[:, i] = anchor + heading / np.linalg.norm(heading) * step
+        anchor = cps[:, i]
+        step = spacing
+        walked = walked + step
+        if cum[seg] < walked:
+            step = walked - cum[seg]
+            seg += 1
+            anchor = seq[:, seg]
+    cps[:, -1] = seq[:, -1]
+    return cps
+
+
+def initial_intermediate_times(waypoint_locations, num_cont_pts):
+    """TG/objectives/objective_variables.py:95-105."""
+    nseg = waypoint_locations.shape[1] - 1
+    if nseg <= 2:
+        return np.array([0.5])
+    cum = np.cumsum(np.linalg.norm(waypoint_locations[:, 1:] - waypoint_locations[:, :-1], 2, 0))
+    return (cum / cum[nseg - 1])[:-1] * (num_cont_pts - 3)
+
+
+def pack_problem(dimension, constraints_container, objective_function_type="minimal_velocity_and_time_path",
+                 num_intervals_free_space_arg=None, initial_control_points_arg=None, initial_scale_factor=None):
+    d = int(dimension)
+    cc = constraints_container
+    wd, db, tb = cc.waypoint_constraints, cc.derivative_constraints, cc.turning_constraint
+    sfc, obstacles = cc.sfc_constraints, cc.obstacle_constraints
+    sw, ew = wd.start_waypoint, wd.end_waypoint
+    if objective_function_type not in OBJECTIVES:
+        raise Exception("Error, Invalid objective function type")
+
+    # ---- sizes (TG/trajectory_generator.py:134-162)
+    mew0 = num_intervals_free_space(wd, num_intervals_free_space_arg)
+    if initial_control_points_arg is not None:
+        nint = np.shape(initial_control_points_arg)[1] - 3
+    elif sfc is not None:
+        nint = sfc.get_num_intervals()
+    else:
+        nint = mew0
+    N = int(nint + 3)
+
+    spec = np.zeros(SP_COUNT, dtype=np.int32)
+    spec[SP_DIM], spec[SP_NCP] = d, N
+    spec[SP_OBJECTIVE] = OBJECTIVES.index(objective_function_type)
+    par = []
+
+    # ---- terminal locations
+    spec[SP_START_KIND] = 1 if sw.checkIfZeroVel() else 0
+    spec[SP_END_KIND] = 1 if ew.checkIfZeroVel() else (2 if ew.is_target else 0)
+    par += [_flat(sw.location), _flat(ew.location)]
+    if spec[SP_END_KIND] == 2:
+        par.append(_flat(ew.velocity))
+
+    # ---- terminal derivative rows (CF/waypoint_constraints.py:73-120)
+    for wp, (f_dir, f_vel, f_acc) in ((sw, (SP_START_DIR, SP_START_VEL, SP_START_ACC)),
+                                      (ew, (SP_END_DIR, SP_END_VEL, SP_END_ACC))):
+        if not wp.checkIfDerivativesActive():
+            continue
+        speed = np.linalg.norm(_flat(wp.velocity)) if wp.checkIfVelocityActive() else None
+        if wp.checkIfDirectionActive():
+            spec[f_dir] = 2 if (speed is not None and speed <= 0) else 1
+            par.append(_flat(wp.direction))
+        if speed is not None and speed > 0:
+            spec[f_vel] = 1
+            par.append(_flat(wp.velocity))
+        if wp.checkIfAccelerationActive():
+            spec[f_acc] = 1
+            par.append(_flat(wp.acceleration))
+        if not (spec[f_dir] or spec[f_vel] or spec[f_acc]):
+            # the reference builds a zero-row NonlinearConstraint here and scipy raises
+            raise IndexError("terminal waypoint needs a velocity, direction or acceleration")
+
+    # ---- intermediate waypoints
+    niw = wd.get_num_intermediate_waypoints()
+    spec[SP_NIW] = niw
+    if niw:
+        par.append(_flat(wd.intermediate_locations))
+        if wd.intermediate_velocities is not None:
+            spec[SP_IW_VEL] = 1
+            par.append(_flat(wd.intermediate_velocities))
+
+    # ---- derivative bounds (CF/derivative_constraints.py:17-121)
+    if db is not None and db.checkIfDerivativesActive():
+        gravity = db.gravity if db.max_acceleration is not None else None      # only read next to max_acceleration
+        for flag, value in ((SP_DB_MINV, db.min_velocity), (SP_DB_MAXV, db.max_velocity),
+                            (SP_DB_UP, db.max_upward_velocity), (SP_DB_HORIZ, db.max_horizontal_velocity),
+                            (SP_DB_MAXA, db.max_acceleration), (SP_DB_GRAV, gravity), (SP_DB_JERK, db.max_jerk)):
+            if value is not None:
+                spec[flag] = 1
+                par.append(np.array([float(value)]))
+    if db is not None and db.checkIfTangentialAccelerationActive():
+        spec[SP_TANG] = 1
+        par.append(np.array([float(db.min_tangential_acceleration), float(db.max_tangential_acceleration)]))
+
+    # ---- turning bound
+    if tb is not None and tb.checkIfTurningBoundActive():
+        spec[SP_TURN] = TURN_KINDS[tb.bound_type]
+        par.append(np.array([float(tb.max_turning_bound)]))
+
+    # ---- safe flight corridors (CF/sfc_constraints.py:7-77)
+    if sfc is not None:
+        ipc = sfc.get_intervals_per_corridor()
+        ipc = [int(ipc)] if np.ndim(ipc) == 0 else [int(v) for v in ipc]
+        if len(ipc) > MAX_CORRIDORS:
+            raise Exception("at most %d corridors are supported" % MAX_CORRIDORS)
+        if sum(ipc) != nint:
+            raise Exception("intervals per corridor do not add up to the number of intervals")
+        spec[SP_NCORR] = len(ipc)
+        spec[SP_IPC0:SP_IPC0 + len(ipc)] = ipc
+        for box in sfc.get_sfc_list()[:len(ipc)]:
+            lo, hi = box.getRotatedBounds()
+            par += [_flat(np.asarray(box.rotation).T), _flat(lo), _flat(hi)]
+
+    # ---- obstacles (CF/obstacle_constraints.py:93-113)
+    if obstacles is not None:
+        K = len(obstacles)
+        spec[SP_NOBST] = K
+        centers = np.array([[float(np.asarray(o.center).flatten()[c]) for o in obstacles] for c in range(d)])
+        par += [centers.flatten(), np.array([float(o.radius) for o in obstacles])]
+
+    par = np.concatenate(par) if par else np.zeros(0)
+    lay = Layout(spec)
+    if lay.P != par.size:
+        raise RuntimeError("parameter row has %d entries, layout expects %d" % (par.size, lay.P))
+    n = lay.n
+
+    # ---- variables (TG/objectives/objective_variables.py:27-61)
+    seq = wd.get_waypoint_locations() if sfc is None else sfc.get_point_sequence()
+    if initial_control_points_arg is not None:
+        cps = np.asarray(initial_control_points_arg, dtype=np.float64)
+    else:
+        cps = initial_control_points(N, seq, d)
+    x0 = np.empty(n)
+    x0[:d * N] = cps.flatten()
+    x0[d * N] = 1.0 if initial_scale_factor is None else initial_scale_factor
+    x0[d * N + 1:d * N + 1 + lay.nws] = 1.0
+    if niw:
+        x0[lay.it0:] = initial_intermediate_times(wd.get_waypoint_locations(), N)
+    xl = np.full(n, -np.inf)
+    xu = np.full(n, np.inf)
+    xl[d * N:d * N + 1 + lay.nws] = VARIABLE_LOWER_BOUND
+    if niw:
+        xl[lay.it0:] = 0.0
+        xu[lay.it0:] = N - 3
+    return PackedProblem(spec, np.ascontiguousarray(par, dtype=np.float64), x0, xl, xu)

@@ -1,0 +1,85 @@
+"""Drop-in ``TrajectoryGenerator`` (reference TG/trajectory_generator.py:46-112) on the CUDA path.
+
+``generate_trajectory`` keeps the reference signature and return value
+``(control_points[d,N], scale_factor, is_violation)``; the SLSQP loop and everything it evaluates
+run on the GPU (one warp per problem).  ``generate_trajectories`` is the batched addition: many
+containers at once, grouped by problem shape, one kernel launch per group.
+"""
+import numpy as np
+
+from . import batch
+from .constraint_data_structures.constraints_container import ConstraintsContainer
+from .constraint_data_structures.waypoint_data import Waypoint
+from .problem import pack_problem
+
+
+class TrajectoryResult:
+    """Per-problem solver outcome that the reference keeps internal (OptimizeResult.status / nit / fun)."""
+
+    def __init__(self, control_points, scale_factor, is_violation, status, nit, fun, x):
+        self.control_points, self.scale_factor, self.is_violation = control_points, scale_factor, is_violation
+        self.status, self.nit, self.fun, self.x = status, nit, fun, x
+        self.success = status == 0
+
+    def __iter__(self):      # unpacks like the reference's return tuple
+        return iter((self.control_points, self.scale_factor, self.is_violation))
+
+
+class TrajectoryGenerator:
+    def __init__(self, dimension: int, jacobian: str = "analytic", maxiter: int = 100, ftol: float = 1e-6):
+        """jacobian: "analytic" (default) or "fd" -- emulate the forward differences scipy applies to the
+        reference's closures, for iterate-level agreement with the reference.  maxiter / ftol default to
+        scipy's SLSQP defaults, which is what the reference runs with (TG/trajectory_generator.py:85)."""
+        self._dimension = dimension
+        self._order = 3
+        self._jacobian, self._maxiter, self._ftol = jacobian, maxiter, ftol
+        self.last_result = None
+
+    # ---- reference API ---------------------------------------------------------------------------
+    def generate_trajectory(self, constraints_container: ConstraintsContainer,
+                            objective_function_type: str = "minimal_velocity_and_time_path",
+                            num_intervals_free_space: int = None,
+                            initial_control_points: np.ndarray = None,
+                            initial_scale_factor: float = None):
+        res = self.generate_trajectories([constraints_container], objective_function_type, num_intervals_free_space,
+                                         [initial_control_points], [initial_scale_factor])[0]
+        self.last_result = res
+        return res.control_points, res.scale_factor, res.is_violation
+
+    def get_terminal_waypoint_properties(self, control_points: np.ndarray, scale_factor: float, side: str):
+        """TG/trajectory_generator.py:99-106 (CF/waypoint_constraints.py:149-203)."""
+        P = np.asarray(control_points, dtype=float)
+        a, b, c = (P[:, 0], P[:, 1], P[:, 2]) if side == "start" else (P[:, -3], P[:, -2], P[:, -1])
+        if side not in ("start", "end"):
+            raise Exception("Funtion does not support this side value")
+        location = (a + 4 * b + c) / 6
+        velocity = (c - a) / (2 * scale_factor)
+        acceleration = (a - 2 * b + c) / (scale_factor * scale_factor)
+        return Waypoint(location=location[:, None], velocity=velocity[:, None], acceleration=acceleration[:, None])
+
+    # ---- batched addition ------------------------------------------------------------------------
+    def generate_trajectories(self, containers, objective_function_type="minimal_velocity_and_time_path",
+                              num_intervals_free_space=None, initial_control_points=None, initial_scale_factors=None):
+        """Solves every container; problems of identical shape share one kernel launch.
+        Returns a list of TrajectoryResult in input order."""
+        count = len(containers)
+        icps = initial_control_points if initial_control_points is not None else [None] * count
+        isfs = initial_scale_factors if initial_scale_factors is not None else [None] * count
+        packed = [pack_problem(self._dimension, cc, objective_function_type, num_intervals_free_space, icps[i], isfs[i])
+                  for i, cc in enumerate(containers)]
+        groups = {}
+        for i, p in enumerate(packed):
+            groups.setdefault(p.key, []).append(i)
+        results = [None] * count
+        for idx in groups.values():
+            first = packed[idx[0]]
+            par = np.stack([packed[i].par for i in idx])
+            x0 = np.stack([np.clip(packed[i].x0, packed[i].xl, packed[i].xu) for i in idx])
+            out = batch.solve_host(first.spec, par, x0, self._maxiter, self._ftol, self._jacobian)
+            lay = first.layout
+            for k, i in enumerate(idx):
+                x = out["x"][k]
+                cps = np.reshape(x[:lay.d * lay.N], (lay.d, lay.N)).copy()
+                results[i] = TrajectoryResult(cps, float(x[lay.ia]), bool(out["violation"][k]), int(out["status"][k]),
+                                              int(out["nit"][k]), float(out["f"][k]), x.copy())
+        return results
