@@ -1,0 +1,365 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path (BASELINE.json): optimised trajectories/s (M2) and constraint+Jacobian
+evaluations/s (M1) on the batched 2-D obstacle-avoidance workload (config C2, 65,536 problems per GPU).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N ...            # the reference's CPU path (scipy SLSQP + its closures)
+
+Prints ONE JSON line (rank 0).  A "step" is one pass of the hot path over one batch: every problem of the
+batch is solved from its initial guess (M2); the same batch is then pushed through the evaluation kernel (M1).
+Multi-GPU: one process per GPU (torchrun), independent problems sharded by rank (weak scaling: every rank owns a
+full batch with its own seed), no collective inside the solve, one NCCL all-gather of the result rows at the end
+of each step.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "optimized_trajectories_per_sec"
+UNIT = "trajectories/s"
+L2_FLUSH_BYTES = 512 << 20
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="C2", help="C2 (default, BASELINE configs[1]) | C3 | C4 | C5a | C5c")
+    ap.add_argument("--batch", type=int, default=None, help="problems per GPU (default: the config's full batch)")
+    ap.add_argument("--jacobian", default="analytic", choices=["analytic", "fd"])
+    ap.add_argument("--cpu-sample", type=int, default=None, help="problems in the CPU baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# --------------------------------------------------------------------------------------------------------------
+# CPU path: the reference's scipy SLSQP call on its own closures (oracle/tg_oracle.py restates the Python closures,
+# the native steps run in the reference's own C++ compiled unmodified when oracle/_ref exists)
+# --------------------------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    name, seed_batch, indices, native_kind = args
+    import warnings
+    warnings.simplefilter("ignore")
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import tg_oracle
+    from trajectory_generator_b200 import synthetic
+    batch = synthetic.make(name, seed_batch)
+    out = []
+    for i in indices:
+        d, cc, kw = synthetic.container_for(batch, i)
+        op = tg_oracle.OracleProblem(d, cc, kw.get("objective_function_type", synthetic.OBJECTIVE[name]),
+                                     kw.get("num_intervals_free_space"), native_kind=native_kind)
+        t = time.perf_counter()
+        res = op.solve()
+        out.append((i, int(res.status), int(res.nit), time.perf_counter() - t, res.x.tolist()))
+    return out
+
+
+def cpu_path_available():
+    ref = os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libTrajectoryConstraints.so"))
+    port = os.path.exists(os.path.join(ROOT, "oracle", "_build", "libtg_oracle.so"))
+    return "ref" if ref else ("oracle" if port else None)
+
+
+def run_cpu_sample(name, gen_batch, sample, procs):
+    """Solves problems [0, sample) of the synthetic batch with a process pool.  Returns (seconds, results)."""
+    import multiprocessing as mp
+    kind = cpu_path_available()
+    if kind is None:
+        raise RuntimeError("oracle libraries are not built (run __graft_entry__.build())")
+    chunks = [list(range(sample))[k::procs] for k in range(procs)]
+    chunks = [c for c in chunks if c]
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(len(chunks)) as pool:
+        pool.map(_noop, range(len(chunks)))            # start the workers before the clock
+        t = time.perf_counter()
+        parts = pool.map(_cpu_worker, [(name, gen_batch, c, kind) for c in chunks])
+        dt = time.perf_counter() - t
+    res = sorted(r for p in parts for r in p)
+    return dt, res, kind
+
+
+def _noop(_):
+    import scipy.optimize  # noqa: F401  (import cost outside the timed region)
+    return 0
+
+
+def cpu_kind_label(kind):
+    # Python closures are the oracle's restatement; with kind 'ref' the native geometry is the reference's own C++
+    return "port"
+
+
+# --------------------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag = index, [], set(), False
+        self.max_mhz = None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [v.strip() for v in out.strip().split(",")]
+                self.samples.append(float(f[0])); self.max_mhz = float(f[1])
+                for n, v in zip(names, f[2:]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    from trajectory_generator_b200 import synthetic
+    name = args.config
+    B = args.batch or synthetic.FULL_BATCH[name]
+    workload = {"C2": "batched 2D obstacle avoidance (test_obstacle_trajectory_2D shape, 8 circular obstacles) x %d problems per GPU",
+                "C3": "batched 2D intermediate-waypoint trajectories with curvature + velocity bounds x %d problems per GPU",
+                "C4": "batched 3D safe-flight-corridor trajectories (4 corridor boxes) x %d problems per GPU",
+                "C5a": "bicycle/unicycle kinematic trajectories, angular-rate + acceleration bounds x %d problems per GPU",
+                "C5c": "bicycle/unicycle kinematic trajectories, curvature + acceleration bounds x %d problems per GPU"}[name] % B
+    cores = os.cpu_count() or 1
+
+    # ---------------------------------------------------------------- reference arm: CPU path only
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        sample = args.cpu_sample or min(256, max(32, 2 * cores))
+        times = []
+        for it in range(args.warmup + args.steps):
+            if it < args.warmup and it > 0:
+                continue                    # one warm-up pass is enough for a process pool
+            dt, res, kind = run_cpu_sample(name, B, sample, cores)
+            if it >= args.warmup:
+                times.append(dt)
+        sec = float(np.mean(times))
+        val = sample / sec
+        st = [r[1] for r in res]
+        line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": workload, "config": name, "sample_per_step": sample,
+                           "solver": "scipy SLSQP (2-point finite differences) on the reference's closures"},
+                "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": cpu_kind_label(kind),
+                                 "native": "reference C++ (oracle/_ref)" if kind == "ref" else "plain-C oracle",
+                                 "sample": "%d problems of the %s batch per step, process pool of %d" % (sample, name, cores),
+                                 "status_histogram": {str(k): int(v) for k, v in zip(*np.unique(st, return_counts=True))}},
+                "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return
+
+    # ---------------------------------------------------------------- CUDA path
+    import torch
+    import torch.distributed as dist
+    from trajectory_generator_b200 import _native, batch as tgb
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product has no CPU path; use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _native.lib()
+
+    # every rank owns a full batch generated with its own seed (weak scaling)
+    gen = {"C2": synthetic.make_c2, "C3": synthetic.make_c3, "C4": synthetic.make_c4}.get(name)
+    if gen is not None:
+        bt = gen(B, seed=synthetic.SEED0 + int(name[1]) + 1000 * rank)
+    else:
+        bt = synthetic.make_c5(B, "angular_rate" if name == "C5a" else "curvature", seed=synthetic.SEED0 + 5 + 1000 * rank)
+    L = bt.layout
+    par_h = torch.from_numpy(bt.par).pin_memory()
+    x0_h = torch.from_numpy(bt.x0).pin_memory()
+    par = par_h.to(dev)
+    x0 = x0_h.to(dev)
+    x = torch.empty_like(x0)
+    bufs = tgb.SolveBuffers(bt.spec, B, dev)
+    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
+    rows = L.n + 4            # result row: x | status | nit | violation | f
+    result = torch.empty((B, rows), dtype=torch.float64, device=dev)
+    gathered = torch.empty((world * B, rows), dtype=torch.float64, device=dev) if world > 1 else None
+
+    def solve_step():
+        out = tgb.solve(bt.spec, par, x, jacobian=args.jacobian, buffers=bufs)
+        if world > 1:
+            result[:, :L.n] = x
+            result[:, L.n] = out["status"]; result[:, L.n + 1] = out["nit"]
+            result[:, L.n + 2] = out["violation"]; result[:, L.n + 3] = out["f"]
+            dist.all_gather_into_tensor(gathered, result)
+
+    def timed(fn, steps, warmup, prepare=None):
+        ev = []
+        for it in range(warmup + steps):
+            if prepare:
+                prepare()
+            flush.fill_(it & 1)                      # evict L2 between iterations
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record(); fn(); e.record()
+            if it >= warmup:
+                ev.append((s, e))
+        torch.cuda.synchronize()
+        return [s.elapsed_time(e) for s, e in ev]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = lib.tg_launch_count()
+    barrier()
+    ms = timed(solve_step, args.steps, args.warmup, prepare=lambda: x.copy_(x0))
+    barrier()
+    solve_launches = (lib.tg_launch_count() - launches0) * args.steps // (args.steps + args.warmup)
+    tot = torch.tensor([sum(ms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tot, op=dist.ReduceOp.MAX)
+    ms_step = tot.item() / args.steps
+    value = world * B / (ms_step * 1e-3)
+    status = bufs.status.cpu().numpy(); nit = bufs.nit.cpu().numpy()
+    x_gpu = x.cpu().numpy()
+
+    # ---- M1: evaluation kernel on the same batch
+    xe = torch.from_numpy(synthetic.evaluation_points(bt)).to(dev)
+    ev_out = {}
+    barrier()
+    ms_e = timed(lambda: tgb.evaluate(bt.spec, par, xe, out=ev_out), args.steps, args.warmup)
+    barrier()
+    tote = torch.tensor([sum(ms_e)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tote, op=dist.ReduceOp.MAX)
+    ms_eval = tote.item() / args.steps
+    eval_bytes = 8 * (L.n + L.P + L.m + L.m_nl * L.n + 1 + L.n)
+
+    # ---- e2e: host buffers through the C-ABI (tg_solve_host / tg_eval_host), copies inside the timed call
+    x_host = bt.x0.copy()
+    e2e_times = []
+    for it in range(1 + min(args.steps, 3)):
+        x_host[:] = bt.x0
+        barrier()
+        t = time.perf_counter()
+        oh = tgb.solve_host(bt.spec, bt.par, x_host, jacobian=args.jacobian)
+        barrier()
+        if it > 0:
+            e2e_times.append(time.perf_counter() - t)
+    e2e_t = torch.tensor([float(np.mean(e2e_times))], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_val = world * B / e2e_t.item()
+    h2d = 8 * B * (L.P + L.n)
+    d2h = 8 * B * (L.n + 1) + 4 * B * 3
+    te = []
+    for it in range(3):
+        t = time.perf_counter()
+        tgb.evaluate_host(bt.spec, bt.par, synthetic.evaluation_points(bt) if it == 0 else xe_h)
+        if it == 0:
+            xe_h = xe.cpu().numpy()
+        else:
+            te.append(time.perf_counter() - t)
+    eval_e2e = world * B / float(np.mean(te))
+    if rank == 0:
+        sampler.stop_flag = True
+        sampler.join(timeout=2)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s (B200_PROFILING.md)"
+    # per-GPU figures for the rooflines (one launch = one batch on one GPU)
+    solve_bytes = 8 * (L.P + 2 * L.n + 4) * B
+    mean_nit = float(nit.mean())
+    # flops model of SURVEY.md 8(d): nit * [F_eval + n_ls F_val + (2 n^3/3 + 2 m n^2)]
+    f_eval = {"C2": 12.5e3, "C3": 22.5e3, "C4": 2.5e3}.get(name, 8.3e3)
+    flops_traj = mean_nit * (1.3 * f_eval + 2.0 * L.n ** 3 / 3 + 2.0 * L.m * L.n ** 2)
+    fp64_peak_tf = 148 * 64 * 2 * 1.965e9 / 1e12
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": workload, "config": name, "problems_per_gpu": B, "n": L.n, "m": L.m, "meq": L.meq,
+                       "maxiter": 100, "ftol": 1e-6, "jacobian": args.jacobian, "l2": "flushed between iterations (512 MiB fill)",
+                       "multi_gpu": "independent problems sharded by rank, one NCCL all-gather of result rows per step"},
+            "solve_stats": {"mean_nit": mean_nit, "max_nit": int(nit.max()),
+                            "status_histogram": {str(k): int(v) for k, v in zip(*np.unique(status, return_counts=True))}},
+            "roofline": {"kernel": "tg_solve_kernel", "bound": "hbm", "achieved": solve_bytes / (ms_step * 1e-3) / 1e9,
+                         "peak": hbm_peak, "unit": "GB/s", "frac": solve_bytes / (ms_step * 1e-3) / 1e9 / hbm_peak,
+                         "traffic": None, "peak_source": peak_src,
+                         "note": "the SQP kernel keeps each problem in shared memory; it is FP64/latency bound, see roofline_fp64"},
+            "roofline_fp64": {"kernel": "tg_solve_kernel", "model_flops_per_trajectory": flops_traj,
+                              "achieved": flops_traj * B / (ms_step * 1e-3) / 1e12, "peak": fp64_peak_tf, "unit": "TFLOP/s",
+                              "frac": flops_traj * B / (ms_step * 1e-3) / 1e12 / fp64_peak_tf,
+                              "peak_source": "148 SMs x 64 DFMA/clk x 2 x 1.965 GHz (nominal; not in MEASURED_PEAKS.json)"},
+            "evals": {"metric": "constraint_jacobian_evaluations_per_sec", "value": world * B / (ms_eval * 1e-3),
+                      "unit": "evaluations/s", "ms_per_step": ms_eval, "bytes_per_eval": eval_bytes,
+                      "e2e": {"value": eval_e2e, "unit": "evaluations/s", "h2d_bytes_per_step": h2d,
+                              "d2h_bytes_per_step": 8 * B * (1 + L.n + L.m + L.m_nl * L.n)},
+                      "roofline": {"kernel": "tg_eval_kernel", "bound": "hbm",
+                                   "achieved": eval_bytes * B / (ms_eval * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                                   "frac": eval_bytes * B / (ms_eval * 1e-3) / 1e9 / hbm_peak, "traffic": None,
+                                   "peak_source": peak_src}},
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "api": "tg_solve_host (C-ABI, host buffers; copies inside the call)"},
+            "gpu_launches": int(solve_launches),
+            "clocks": sampler.summary()}
+
+    # ---- CPU baseline on the box's host cores (rank 0, N = 1 only): bounded sample of the same problems
+    if world == 1 and not args.no_cpu_baseline and cpu_path_available():
+        sample = args.cpu_sample or min(256, max(32, 2 * cores))
+        try:
+            dt, res, kind = run_cpu_sample(name, B, sample, cores)
+            st_ref = np.array([r[1] for r in res]); x_ref = np.array([r[4] for r in res])
+            k = L.ia + 1
+            dcp = np.abs(x_gpu[:sample, :k] - x_ref[:, :k]).max(1)
+            both0 = (st_ref == 0) & (status[:sample] == 0)
+            line["cpu_baseline"] = {"value": sample / dt, "unit": UNIT, "cores": cores, "kind": cpu_kind_label(kind),
+                                    "native": "reference C++ (oracle/_ref)" if kind == "ref" else "plain-C oracle",
+                                    "sample": "first %d problems of the same batch, scipy SLSQP with 2-point finite differences, process pool of %d" % (sample, cores),
+                                    "seconds": dt,
+                                    "status_histogram": {str(a): int(b) for a, b in zip(*np.unique(st_ref, return_counts=True))}}
+            line["parity_sample"] = {"problems": int(sample), "reference_status0": int((st_ref == 0).sum()),
+                                     "both_status0": int(both0.sum()),
+                                     "status0_within_1e-5": int((dcp[both0] <= 1e-5).sum()),
+                                     "status0_within_1e-3": int((dcp[both0] <= 1e-3).sum()),
+                                     "jacobian": args.jacobian}
+        except Exception as exc:      # the baseline is reported, never required
+            line["cpu_baseline"] = {"error": repr(exc)}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
