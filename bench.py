@@ -40,6 +40,7 @@ def parse():
     ap.add_argument("--jacobian", default="analytic", choices=["analytic", "fd"])
     ap.add_argument("--cpu-sample", type=int, default=None, help="problems in the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--fused", action="store_true", help="one persistent solve kernel instead of lock-step stage kernels")
     return ap.parse_args()
 
 
@@ -204,7 +205,7 @@ def main():
     gathered = torch.empty((world * B, rows), dtype=torch.float64, device=dev) if world > 1 else None
 
     def solve_step():
-        out = tgb.solve(bt.spec, par, x, jacobian=args.jacobian, buffers=bufs)
+        out = tgb.solve(bt.spec, par, x, jacobian=args.jacobian, buffers=bufs, fused=args.fused)
         if world > 1:
             result[:, :L.n] = x
             result[:, L.n] = out["status"]; result[:, L.n + 1] = out["nit"]
@@ -264,7 +265,7 @@ def main():
         x_host[:] = bt.x0
         barrier()
         t = time.perf_counter()
-        oh = tgb.solve_host(bt.spec, bt.par, x_host, jacobian=args.jacobian)
+        oh = tgb.solve_host(bt.spec, bt.par, x_host, jacobian=args.jacobian, fused=args.fused)
         barrier()
         if it > 0:
             e2e_times.append(time.perf_counter() - t)
@@ -310,7 +311,7 @@ def main():
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
             "config": {"workload": workload, "config": name, "problems_per_gpu": B, "n": L.n, "m": L.m, "meq": L.meq,
-                       "maxiter": 100, "ftol": 1e-6, "jacobian": args.jacobian, "l2": "flushed between iterations (512 MiB fill)",
+                       "maxiter": 100, "ftol": 1e-6, "jacobian": args.jacobian, "schedule": "fused persistent kernel" if args.fused else "lock-step stage kernels", "l2": "flushed between iterations (512 MiB fill)",
                        "multi_gpu": "independent problems sharded by rank, one NCCL all-gather of result rows per step"},
             "solve_stats": {"mean_nit": mean_nit, "max_nit": int(nit.max()),
                             "status_histogram": {str(k): int(v) for k, v in zip(*np.unique(status, return_counts=True))}},

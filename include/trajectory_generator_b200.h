@@ -58,8 +58,9 @@ int tg_linear_rows_batch(const int *spec, int B, const double *par, double *alin
 
 /* flags for tg_solve_batch */
 #define TG_SOLVE_FD_JACOBIAN 1   /* emulate scipy's forward differences (h = 1.4901161193847656e-08) */
+#define TG_SOLVE_FUSED 2         /* one persistent kernel (a warp runs a whole solve) instead of lock-step stage kernels */
 
-/* bytes of device scratch tg_solve_batch needs for this shape (0 if it all fits in shared memory) */
+/* bytes of device scratch tg_solve_batch needs for this shape and batch size */
 size_t tg_solve_workspace_bytes(const int *spec, int B);
 
 /*

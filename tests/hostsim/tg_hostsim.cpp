@@ -29,11 +29,10 @@ extern "C" void hs_eval(const int *spec, const double *par, const double *x, dou
     *f = tg_objective(L, spec, x, g);
     TgJac sink = {J, L.n, 1, 0};
     if (J) {
-        tg_linear_jacobian(L, spec, par, sink);
-        tg_constraints(L, spec, par, x, c, &sink, scratch.data());
-    } else {
-        tg_constraints(L, spec, par, x, c, nullptr, scratch.data());
+        if (L.d == 2) tg_linear_jacobian_d<2>(L, spec, par, sink); else tg_linear_jacobian_d<3>(L, spec, par, sink);
     }
+    if (L.d == 2) tg_constraints_d<2>(L, spec, par, x, c, J ? &sink : nullptr, scratch.data());
+    else tg_constraints_d<3>(L, spec, par, x, c, J ? &sink : nullptr, scratch.data());
 }
 
 #ifdef TG_WITH_SQP
@@ -45,7 +44,8 @@ extern "C" int hs_solve(const int *spec, const double *par, double *x, int maxit
     size_t nd = tg_sqp_workspace_doubles(L);
     std::vector<double> ws(nd);
     TgSqpResult res;
-    tg_sqp_solve(L, spec, par, x, ws.data(), maxiter, ftol, flags, &res, trace, trace_cap);
+    if (L.d == 2) tg_sqp_solve<2>(L, spec, par, x, ws.data(), maxiter, ftol, flags, &res, trace, trace_cap);
+    else tg_sqp_solve<3>(L, spec, par, x, ws.data(), maxiter, ftol, flags, &res, trace, trace_cap);
     *fout = res.f; *status = res.status; *nit = res.nit; *nfev = res.nfev;
     return res.status;
 }

@@ -69,3 +69,15 @@ def test_solve_matches_hostsim(native_lib, hostsim, name):
     if ref["status"] == 0 and name not in ("bicycle3",):
         assert int(out["status"][0]) == 0
         assert np.abs(out["x"][0][:L.ia + 1] - ref["x"][:L.ia + 1]).max() <= 1e-5
+
+
+def test_fused_and_lockstep_kernels_agree(native_lib):
+    """Same stage functions, two schedules (one persistent kernel vs lock-step stage kernels): identical results."""
+    from trajectory_generator_b200 import batch, synthetic as syn
+    for name in ("C2", "C4"):
+        b = syn.make(name, 512)
+        a = batch.solve_host(b.spec, b.par, b.x0)
+        f = batch.solve_host(b.spec, b.par, b.x0, fused=True)
+        assert np.array_equal(a["status"], f["status"]) and np.array_equal(a["nit"], f["nit"])
+        assert np.array_equal(a["x"], f["x"])
+        assert (a["status"] == 0).mean() > 0.7

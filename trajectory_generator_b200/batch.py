@@ -88,9 +88,15 @@ class SolveBuffers:
         self.ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
 
 
-def solve(spec, par, x, maxiter=100, ftol=1e-6, jacobian="analytic", buffers=None):
+def _flags(jacobian, fused):
+    return JACOBIAN_MODES[jacobian] | (2 if fused else 0)
+
+
+def solve(spec, par, x, maxiter=100, ftol=1e-6, jacobian="analytic", buffers=None, fused=False):
     """Device-resident M2 solve.  x [B,n] is overwritten with the optimised variables.
-    Returns dict(x, f, status, nit, violation) of CUDA tensors."""
+    Returns dict(x, f, status, nit, violation) of CUDA tensors.
+    fused=False (default): lock-step stage kernels over the whole batch; fused=True: one persistent kernel in
+    which each warp runs a whole solve (same arithmetic, kept for comparison)."""
     torch = _torch()
     lay = Layout(spec)
     if not (par.is_cuda and x.is_cuda):
@@ -102,7 +108,7 @@ def solve(spec, par, x, maxiter=100, ftol=1e-6, jacobian="analytic", buffers=Non
     buf = buffers if buffers is not None else SolveBuffers(spec, B, dev)
     with torch.cuda.device(dev):
         rc = _native.lib().tg_solve_batch(buf.sp, B, _ptr(par), _ptr(x), _ptr(buf.f), _ptr(buf.status), _ptr(buf.nit),
-                                          _ptr(buf.violation), int(maxiter), float(ftol), JACOBIAN_MODES[jacobian],
+                                          _ptr(buf.violation), int(maxiter), float(ftol), _flags(jacobian, fused),
                                           _ptr(buf.ws), buf.ws.numel(), _stream(torch, dev))
     _native.check(rc, "tg_solve_batch")
     return dict(x=x, f=buf.f, status=buf.status, nit=buf.nit, violation=buf.violation)
@@ -127,7 +133,7 @@ def evaluate_host(spec, par, x, want=("f", "g", "c", "jnl")):
     return res
 
 
-def solve_host(spec, par, x0, maxiter=100, ftol=1e-6, jacobian="analytic"):
+def solve_host(spec, par, x0, maxiter=100, ftol=1e-6, jacobian="analytic", fused=False):
     """Host-buffer M2 solve through tg_solve_host.  Returns dict(x, f, status, nit, violation) of numpy arrays."""
     lay = Layout(spec)
     par = np.ascontiguousarray(par, dtype=np.float64).reshape(-1, lay.P)
@@ -137,6 +143,6 @@ def solve_host(spec, par, x0, maxiter=100, ftol=1e-6, jacobian="analytic"):
     viol = np.empty(B, dtype=np.int32)
     spec, sp = _native.spec_ptr(spec)
     rc = _native.lib().tg_solve_host(sp, B, _np_ptr(par), _np_ptr(x), _np_ptr(f), _np_ptr(status), _np_ptr(nit),
-                                     _np_ptr(viol), int(maxiter), float(ftol), JACOBIAN_MODES[jacobian])
+                                     _np_ptr(viol), int(maxiter), float(ftol), _flags(jacobian, fused))
     _native.check(rc, "tg_solve_host")
     return dict(x=x, f=f, status=status, nit=nit, violation=viol)

@@ -56,12 +56,14 @@ static int tg_make_shape(const int *spec, TgShape *S)
 // M1 evaluation kernel
 // ---------------------------------------------------------------------------
 constexpr int EVAL_WARPS = 4;
+constexpr int SOLVE_MIN_CTAS = 4;      // 4 CTAs x 4 warps per SM -> at most 128 registers per thread
 
 __device__ __forceinline__ int tg_eval_smem_doubles(const TgLayout &L)
 {
     return L.n + L.P + L.m + tg_scratch_doubles(L) + 4;
 }
 
+template <int D>
 __global__ void __launch_bounds__(EVAL_WARPS * 32)
 tg_eval_kernel(const TgShape S, int B, const double *__restrict__ par, const double *__restrict__ x,
                double *__restrict__ f, double *__restrict__ g, double *__restrict__ c, double *__restrict__ jnl)
@@ -80,7 +82,7 @@ tg_eval_kernel(const TgShape S, int B, const double *__restrict__ par, const dou
         if (f && lane == 0) f[b] = fv;
         if (c || jnl) {
             TgJac sink = {jnl ? jnl + (size_t)b * L.m_nl * L.n : nullptr, L.n, 1, 1};
-            tg_constraints(L, S.sp, sp_, sx, sc, jnl ? &sink : nullptr, scr);
+            tg_constraints_d<D>(L, S.sp, sp_, sx, sc, jnl ? &sink : nullptr, scr);
             if (c)
                 for (int j = lane; j < L.m; j += 32) c[(size_t)b * L.m + j] = sc[j];
         }
@@ -88,6 +90,7 @@ tg_eval_kernel(const TgShape S, int B, const double *__restrict__ par, const dou
     }
 }
 
+template <int D>
 __global__ void __launch_bounds__(EVAL_WARPS * 32)
 tg_linear_kernel(const TgShape S, int B, const double *__restrict__ par, double *__restrict__ alin)
 {
@@ -100,7 +103,7 @@ tg_linear_kernel(const TgShape S, int B, const double *__restrict__ par, double 
         for (int i = lane; i < L.P; i += 32) sp_[i] = par[(size_t)b * L.P + i];
         __syncwarp();
         TgJac sink = {alin + (size_t)b * L.m * L.n, L.n, 1, 0};
-        tg_linear_jacobian(L, S.sp, sp_, sink);
+        tg_linear_jacobian_d<D>(L, S.sp, sp_, sink);
         __syncwarp();
     }
 }
@@ -132,7 +135,9 @@ __device__ int tg_last_block_violation(const TgLayout &L, const double *c)
     return __any_sync(0xffffffffu, bad);
 }
 
-__global__ void tg_solve_kernel(const TgShape S, int B, const double *__restrict__ par, double *__restrict__ x,
+template <int D>
+__global__ void __launch_bounds__(128, SOLVE_MIN_CTAS)
+tg_solve_kernel(const TgShape S, int B, const double *__restrict__ par, double *__restrict__ x,
                                 double *__restrict__ fout, int *__restrict__ status, int *__restrict__ nit,
                                 int *__restrict__ violation, int maxiter, double ftol, int flags,
                                 double *gws, size_t ws_doubles, int warps_per_cta, int *queue)
@@ -151,7 +156,7 @@ __global__ void tg_solve_kernel(const TgShape S, int B, const double *__restrict
         for (int i = lane; i < L.P; i += 32) spar[i] = par[(size_t)b * L.P + i];
         __syncwarp();
         TgSqpResult res;
-        tg_sqp_solve(L, S.sp, spar, x + (size_t)b * L.n, ws, maxiter, ftol, flags, &res, nullptr, 0);
+        tg_sqp_solve<D>(L, S.sp, spar, x + (size_t)b * L.n, ws, maxiter, ftol, flags, &res, nullptr, 0);
         res.status = __shfl_sync(0xffffffffu, res.status, 0);
         int viol = 0;
         if (res.status != 0) {
@@ -182,7 +187,7 @@ extern "C" int tg_device_check(void)
     int dev = 0;
     TG_CUDA(cudaGetDevice(&dev));
     cudaFuncAttributes attr;
-    e = cudaFuncGetAttributes(&attr, tg_eval_kernel);
+    e = cudaFuncGetAttributes(&attr, tg_eval_kernel<2>);
     if (e != cudaSuccess) return tg_fail(11, "no kernel image for this device (built for sm_100a)", e);
     TG_CUDA(cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev));
     TG_CUDA(cudaDeviceGetAttribute(&g_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
@@ -215,11 +220,13 @@ extern "C" int tg_eval_batch(const int *spec, int B, const double *par, const do
     if ((rc = tg_device_check())) return rc;
     const size_t smem = (size_t)EVAL_WARPS * (S.L.n + S.L.P + S.L.m + tg_scratch_doubles(S.L) + 4) * sizeof(double);
     if (smem > (size_t)g_smem_optin) return tg_fail(3, "problem shape too large for the evaluation kernel's shared memory");
-    TG_CUDA(cudaFuncSetAttribute(tg_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (S.L.d == 2) TG_CUDA(cudaFuncSetAttribute(tg_eval_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    else TG_CUDA(cudaFuncSetAttribute(tg_eval_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int grid = (B + EVAL_WARPS - 1) / EVAL_WARPS;
     const int cap = g_sm_count * 16;
     if (grid > cap) grid = cap;
-    tg_eval_kernel<<<grid, EVAL_WARPS * 32, smem, (cudaStream_t)stream>>>(S, B, par, x, f, g, c, jnl);
+    if (S.L.d == 2) tg_eval_kernel<2><<<grid, EVAL_WARPS * 32, smem, (cudaStream_t)stream>>>(S, B, par, x, f, g, c, jnl);
+    else tg_eval_kernel<3><<<grid, EVAL_WARPS * 32, smem, (cudaStream_t)stream>>>(S, B, par, x, f, g, c, jnl);
     g_launches++;
     TG_CUDA(cudaGetLastError());
     return 0;
@@ -236,17 +243,102 @@ extern "C" int tg_linear_rows_batch(const int *spec, int B, const double *par, d
     int grid = (B + EVAL_WARPS - 1) / EVAL_WARPS;
     const int cap = g_sm_count * 16;
     if (grid > cap) grid = cap;
-    tg_linear_kernel<<<grid, EVAL_WARPS * 32, smem, (cudaStream_t)stream>>>(S, B, par, alin);
+    if (S.L.d == 2) tg_linear_kernel<2><<<grid, EVAL_WARPS * 32, smem, (cudaStream_t)stream>>>(S, B, par, alin);
+    else tg_linear_kernel<3><<<grid, EVAL_WARPS * 32, smem, (cudaStream_t)stream>>>(S, B, par, alin);
     g_launches++;
     TG_CUDA(cudaGetLastError());
     return 0;
 }
 
-// launch geometry of the solve kernel for a shape
+// ---------------------------------------------------------------------------
+// M2, lock-step form: the two stages of tg_sqp.h as separate kernels over the whole batch.  Every warp of
+// the machine then runs the same few functions at the same time (the fused kernel is bound by
+// instruction-cache misses: each warp sits in a different phase of a ~300 KB program).  Per-problem state
+// lives in a global workspace and is staged through shared memory inside a stage when it fits.
+// ---------------------------------------------------------------------------
+constexpr int STAGE_WARPS = 4;
+
+template <int D>
+__global__ void __launch_bounds__(STAGE_WARPS * 32)
+tg_sqp_begin_kernel(const TgShape S, int B, const double *__restrict__ x, double *pws, size_t np, int maxiter, double ftol,
+                    int flags)
+{
+    const int warp = threadIdx.x >> 5;
+    const int b = blockIdx.x * STAGE_WARPS + warp;
+    if (b >= B) return;
+    TgSqpWs W;
+    size_t a, c;
+    tg_sqp_carve2(S.L, pws + (size_t)b * np, nullptr, &W, &a, &c);
+    tg_sqp_begin(S.L, W, x + (size_t)b * S.L.n, maxiter, ftol, flags);
+}
+
+// STAGE 0: line search / first evaluation.  STAGE 1: update + QP.
+template <int D, int STAGE>
+__global__ void __launch_bounds__(STAGE_WARPS * 32, 4)
+tg_sqp_stage_kernel(const TgShape S, int B, const double *__restrict__ par, double *pws, size_t np, size_t ns, int staged,
+                    int *counters)
+{
+    extern __shared__ double smem[];
+    const TgLayout &L = S.L;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int b = blockIdx.x * STAGE_WARPS + warp;
+    if (b >= B) return;
+    double *gp = pws + (size_t)b * np;
+    const int st = ((const TgSqpCtl *)gp)->state;
+    if (STAGE == 0 ? !(st == TG_ST_INIT || st == TG_ST_LS) : !(st == TG_ST_UPDATE || st == TG_ST_QP)) return;
+    const size_t per = (size_t)L.P + 1 + ns + (staged ? np : 0);
+    double *spar = smem + (size_t)warp * per, *sscr = spar + L.P + 1, *spers = sscr + ns;
+    if (STAGE == 0)
+        for (int i = lane; i < L.P; i += 32) spar[i] = par[(size_t)b * L.P + i];
+    if (staged)
+        for (size_t i = lane; i < np; i += 32) spers[i] = gp[i];
+    __syncwarp();
+    TgSqpWs W;
+    size_t a, c;
+    tg_sqp_carve2(L, staged ? spers : gp, sscr, &W, &a, &c);
+    if (STAGE == 0) tg_sqp_stage_ls<D>(L, S.sp, spar, W, nullptr, 0);
+    else tg_sqp_stage_qp(L, W);
+    __syncwarp();
+    if (STAGE == 1 && lane == 0 && W.ctl->state == TG_ST_DONE) atomicAdd(counters, 1);
+    if (staged)
+        for (size_t i = lane; i < np; i += 32) gp[i] = spers[i];
+}
+
+__global__ void tg_sqp_finish_kernel(const TgShape S, int B, const double *pws, size_t np, double *__restrict__ x,
+                                     double *__restrict__ fout, int *__restrict__ status, int *__restrict__ nit,
+                                     int *__restrict__ violation)
+{
+    const TgLayout &L = S.L;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int b = blockIdx.x * STAGE_WARPS + warp;
+    if (b >= B) return;
+    TgSqpWs W;
+    size_t a, c;
+    tg_sqp_carve2(L, const_cast<double *>(pws) + (size_t)b * np, nullptr, &W, &a, &c);
+    for (int i = lane; i < L.n; i += 32) x[(size_t)b * L.n + i] = W.x[i];
+    const TgSqpCtl ctl = *W.ctl;
+    int viol = 0;
+    if (ctl.status != 0) viol = tg_last_block_violation(L, W.c);
+    if (lane == 0) {
+        if (status) status[b] = ctl.status;
+        if (nit) nit[b] = ctl.iter > ctl.maxiter ? ctl.maxiter : ctl.iter;
+        if (fout) fout[b] = ctl.f;
+        if (violation) violation[b] = viol;
+    }
+}
+
+// launch geometry for a shape
 struct TgSolvePlan {
+    // fused kernel
     int warps_per_cta, ctas, use_global;
     size_t ws_doubles, smem_bytes, global_bytes;
+    // lock-step kernels
+    size_t np, ns, stage_smem;
+    int staged, chunk;
+    size_t phased_bytes;
 };
+
+#define TG_PHASED_CHUNK_BYTES ((size_t)6 << 30)     // per-chunk cap of the global state (problems are solved in chunks)
 
 static int tg_plan_solve(const TgShape &S, int B, TgSolvePlan *P)
 {
@@ -280,6 +372,19 @@ static int tg_plan_solve(const TgShape &S, int B, TgSolvePlan *P)
         P->ctas = need > 0 ? need : 1;
         if (P->use_global) P->global_bytes = (size_t)P->ctas * P->warps_per_cta * P->ws_doubles * sizeof(double);
     }
+    // lock-step plan: stage the persistent state through shared memory when 16 warps still fit on an SM
+    P->np = tg_sqp_persistent_doubles(S.L);
+    P->ns = tg_sqp_scratch_doubles(S.L);
+    const size_t with_state = ((size_t)S.L.P + 1 + P->ns + P->np) * sizeof(double) * STAGE_WARPS;
+    const size_t without = ((size_t)S.L.P + 1 + P->ns) * sizeof(double) * STAGE_WARPS;
+    P->staged = with_state * 4 <= sm_total - 4096;
+    P->stage_smem = P->staged ? with_state : without;
+    if (P->stage_smem > budget) return tg_fail(3, "problem shape too large for the solve kernels' shared memory");
+    size_t chunk = TG_PHASED_CHUNK_BYTES / (P->np * sizeof(double));
+    if (chunk < 1024) chunk = 1024;
+    if (chunk > (size_t)B) chunk = (size_t)B;
+    P->chunk = (int)chunk;
+    P->phased_bytes = chunk * P->np * sizeof(double);
     return 0;
 }
 
@@ -288,7 +393,58 @@ extern "C" size_t tg_solve_workspace_bytes(const int *spec, int B)
     TgShape S;
     TgSolvePlan P;
     if (tg_make_shape(spec, &S) || tg_plan_solve(S, B, &P)) return 0;
-    return P.global_bytes + 256;     // + the work queue counter
+    const size_t need = P.global_bytes > P.phased_bytes ? P.global_bytes : P.phased_bytes;
+    return need + 256;     // + counters
+}
+
+template <int D>
+static int tg_solve_fused(const TgShape &S, const TgSolvePlan &P, int B, const double *par, double *x, double *f,
+                          int *status, int *nit, int *violation, int maxiter, double ftol, int flags, int *queue,
+                          double *gws, cudaStream_t st)
+{
+    TG_CUDA(cudaFuncSetAttribute(tg_solve_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.smem_bytes));
+    tg_solve_kernel<D><<<P.ctas, P.warps_per_cta * 32, P.smem_bytes, st>>>(S, B, par, x, f, status, nit, violation, maxiter,
+                                                                           ftol, flags, P.use_global ? gws : nullptr,
+                                                                           P.ws_doubles, P.warps_per_cta, queue);
+    g_launches++;
+    TG_CUDA(cudaGetLastError());
+    return 0;
+}
+
+template <int D>
+static int tg_solve_phased(const TgShape &S, const TgSolvePlan &P, int B, const double *par, double *x, double *f,
+                           int *status, int *nit, int *violation, int maxiter, double ftol, int flags, int *counters,
+                           double *pws, cudaStream_t st)
+{
+    TG_CUDA(cudaFuncSetAttribute(tg_sqp_stage_kernel<D, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.stage_smem));
+    TG_CUDA(cudaFuncSetAttribute(tg_sqp_stage_kernel<D, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.stage_smem));
+    const TgLayout &L = S.L;
+    for (int lo = 0; lo < B; lo += P.chunk) {
+        const int nb = B - lo < P.chunk ? B - lo : P.chunk;
+        const int grid = (nb + STAGE_WARPS - 1) / STAGE_WARPS;
+        const double *cpar = par + (size_t)lo * L.P;
+        double *cx = x + (size_t)lo * L.n;
+        TG_CUDA(cudaMemsetAsync(counters, 0, 256, st));
+        tg_sqp_begin_kernel<D><<<grid, STAGE_WARPS * 32, 0, st>>>(S, nb, cx, pws, P.np, maxiter, ftol, flags);
+        g_launches++;
+        int done = 0;
+        // each round = one SLSQP major iteration of every unfinished problem; maxiter + 1 rounds finish everything
+        for (int round = 0; round <= maxiter + 1 && done < nb; round++) {
+            tg_sqp_stage_kernel<D, 0><<<grid, STAGE_WARPS * 32, P.stage_smem, st>>>(S, nb, cpar, pws, P.np, P.ns, P.staged, counters);
+            tg_sqp_stage_kernel<D, 1><<<grid, STAGE_WARPS * 32, P.stage_smem, st>>>(S, nb, cpar, pws, P.np, P.ns, P.staged, counters);
+            g_launches += 2;
+            if ((round & 7) == 7) {      // poll the number of finished problems
+                TG_CUDA(cudaMemcpyAsync(&done, counters, sizeof(int), cudaMemcpyDeviceToHost, st));
+                TG_CUDA(cudaStreamSynchronize(st));
+            }
+        }
+        tg_sqp_finish_kernel<<<grid, STAGE_WARPS * 32, 0, st>>>(S, nb, pws, P.np, cx, f ? f + lo : nullptr,
+                                                               status ? status + lo : nullptr, nit ? nit + lo : nullptr,
+                                                               violation ? violation + lo : nullptr);
+        g_launches++;
+        TG_CUDA(cudaGetLastError());
+    }
+    return 0;
 }
 
 extern "C" int tg_solve_batch(const int *spec, int B, const double *par, double *x, double *f, int *status, int *nit,
@@ -302,18 +458,18 @@ extern "C" int tg_solve_batch(const int *spec, int B, const double *par, double 
     if (B <= 0) return 0;
     if ((rc = tg_plan_solve(S, B, &P))) return rc;
     if (S.L.n > 62) return tg_fail(3, "more than 62 optimisation variables are not supported by the solve kernel");
-    if (!workspace || workspace_bytes < P.global_bytes + 256) return tg_fail(4, "workspace too small (see tg_solve_workspace_bytes)");
-    int *queue = (int *)workspace;
-    double *gws = P.use_global ? (double *)((char *)workspace + 256) : nullptr;
+    const size_t need = (P.global_bytes > P.phased_bytes ? P.global_bytes : P.phased_bytes) + 256;
+    if (!workspace || workspace_bytes < need) return tg_fail(4, "workspace too small (see tg_solve_workspace_bytes)");
+    int *counters = (int *)workspace;
+    double *gws = (double *)((char *)workspace + 256);
     cudaStream_t st = (cudaStream_t)stream;
-    TG_CUDA(cudaMemsetAsync(queue, 0, 256, st));
-    TG_CUDA(cudaFuncSetAttribute(tg_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.smem_bytes));
-    tg_solve_kernel<<<P.ctas, P.warps_per_cta * 32, P.smem_bytes, st>>>(S, B, par, x, f, status, nit, violation, maxiter,
-                                                                        ftol, flags, gws, P.ws_doubles,
-                                                                        P.warps_per_cta, queue);
-    g_launches++;
-    TG_CUDA(cudaGetLastError());
-    return 0;
+    if (flags & TG_SOLVE_FUSED) {
+        TG_CUDA(cudaMemsetAsync(counters, 0, 256, st));
+        return S.L.d == 2 ? tg_solve_fused<2>(S, P, B, par, x, f, status, nit, violation, maxiter, ftol, flags, counters, gws, st)
+                          : tg_solve_fused<3>(S, P, B, par, x, f, status, nit, violation, maxiter, ftol, flags, counters, gws, st);
+    }
+    return S.L.d == 2 ? tg_solve_phased<2>(S, P, B, par, x, f, status, nit, violation, maxiter, ftol, flags, counters, gws, st)
+                      : tg_solve_phased<3>(S, P, B, par, x, f, status, nit, violation, maxiter, ftol, flags, counters, gws, st);
 }
 
 // ---------------------------------------------------------------------------

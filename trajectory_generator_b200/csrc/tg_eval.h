@@ -26,8 +26,9 @@
 #define TG_PI 3.14159265358979323846
 
 // TG_HD (tg_spec.h) force-inlines small helpers; TG_FN is for the large block evaluators
+// (kept out of line on the device: the kernels are instruction-cache bound when everything is inlined)
 #if defined(__CUDACC__)
-#define TG_FN __host__ __device__ inline
+#define TG_FN __host__ __device__ __noinline__
 #else
 #define TG_FN static inline
 #endif
@@ -352,6 +353,7 @@ TG_FN double tg_interval_turn_bound(const TgInterval<D> &I, double al, int kind,
     }
     const int p = kind == TG_TURN_CURVATURE ? 2 : kind == TG_TURN_ANGULAR_RATE ? 1 : 0;
     double vp = 1;   // vmin^p
+    #pragma unroll 1
     for (int q = 0; q < p; q++) vp *= vmin;
     const double b1 = amax / vp, b2 = cmax / (vp * vmin);
     const bool use2 = b2 < b1;
@@ -502,6 +504,7 @@ TG_FN double tg_objective(const TgLayout &L, const int *sp, const double *x, dou
     double S = 0;
     if (k) {
         const int nd = N - k;
+        #pragma unroll 1
         for (int q = lane; q < d * nd; q += TG_NL) {
             const int c = q / nd, j = q - c * nd;
             const double dd = tg_diff(x + c * N, k, j);
@@ -517,12 +520,14 @@ TG_FN double tg_objective(const TgLayout &L, const int *sp, const double *x, dou
     default: wS = -1; f = 100 * al * al - S; dfa = 200 * al; break;
     }
     if (g) {
+        #pragma unroll 1
         for (int q = lane; q < L.n; q += TG_NL) {
             double v = 0;
             if (q < d * N) {
                 if (k) {
                     const int c = q / N, i = q - c * N;
                     double s = 0;
+                    #pragma unroll 1
                     for (int t = 0; t <= k; t++) {
                         const int j = i - t;
                         if (j >= 0 && j < N - k) s += tg_stencil(k, t) * tg_diff(x + c * N, k, j);
@@ -544,6 +549,7 @@ TG_FN double tg_objective(const TgLayout &L, const int *sp, const double *x, dou
 TG_FN void tg_rows_location(const TgLayout &L, const int *sp, const double *par, const double *x, double *c)
 {
     const int d = L.d, N = L.N, lane = TG_LANE();
+    #pragma unroll 1
     for (int q = lane; q < L.n_start + L.n_end; q += TG_NL) {
         const bool start = q < L.n_start;
         const int r = start ? q : q - L.n_start;
@@ -567,11 +573,13 @@ TG_FN void tg_jac_location(const TgLayout &L, const int *sp, const double *par, 
 {
     const int d = L.d, N = L.N, lane = TG_LANE();
     (void)d;
+    #pragma unroll 1
     for (int q = lane; q < L.n_start + L.n_end; q += TG_NL) {
         const bool start = q < L.n_start;
         const int r = start ? q : q - L.n_start;
         const int kind = start ? sp[TG_SP_START_KIND] : sp[TG_SP_END_KIND];
         double *row = J.p + ((start ? L.r_start : L.r_end) + r) * J.rs;
+        #pragma unroll 1
         for (int i = 0; i < L.n; i++) row[i * J.cs] = 0;
         if (kind == 1) {
             const int i = r / 3, l = r - 3 * i;
@@ -590,10 +598,12 @@ TG_FN void tg_rows_terminal(const TgLayout &L, const int *sp, const double *par,
 {
     const int d = L.d, N = L.N, lane = TG_LANE();
     const double al = x[L.ia];
+    #pragma unroll 1
     for (int side = 0; side < 2; side++) {
         const int dirk = sp[side ? TG_SP_END_DIR : TG_SP_START_DIR];
         const int velon = sp[side ? TG_SP_END_VEL : TG_SP_START_VEL], accon = sp[side ? TG_SP_END_ACC : TG_SP_START_ACC];
         const int nrows = side ? L.n_eder : L.n_sder, r0 = side ? L.r_eder : L.r_sder;
+        #pragma unroll 1
         for (int q = lane; q < nrows; q += TG_NL) {
             int blk = q / d;
             const int c = q - blk * d;
@@ -640,6 +650,7 @@ TG_FN void tg_rows_intermediate(const TgLayout &L, const int *sp, const double *
     const int d = L.d, N = L.N, niw = L.niw, lane = TG_LANE();
     const double al = x[L.ia];
     const int nitems = d * niw * (sp[TG_SP_IW_VEL] ? 2 : 1);
+    #pragma unroll 1
     for (int q = lane; q < nitems; q += TG_NL) {
         const int vel = q >= d * niw;
         const int qq = vel ? q - d * niw : q;
@@ -722,6 +733,7 @@ TG_FN void tg_rows_derivative(const TgLayout &L, const int *sp, const double *pa
     if (sp[TG_SP_DB_MINV]) {
         // min speed over the spline: CC/src/DerivativeBounds.cpp:12-27
         double best = DBL_MAX, tbest = 0; int jb = 0x7fffffff;
+        #pragma unroll 1
         for (int j = lane; j < nint; j += TG_NL) {
             TgInterval<D> I; double v, t;
             tg_load_interval<D>(x, N, j, I);
@@ -750,6 +762,7 @@ TG_FN void tg_rows_derivative(const TgLayout &L, const int *sp, const double *pa
     if (sp[TG_SP_DB_MAXV]) {
         const int npt = 2 * nint + 1;
         // which = 0: max |b|, 1: -min b_z (upward), 2: max |b_xy| (horizontal)
+        #pragma unroll 1
         for (int which = 0; which < 3; which++) {
             if (which == 1 && !sp[TG_SP_DB_UP]) continue;
             if (which == 2 && !sp[TG_SP_DB_HORIZ]) continue;
@@ -758,6 +771,7 @@ TG_FN void tg_rows_derivative(const TgLayout &L, const int *sp, const double *pa
             // (CF/derivative_constraints.py:38-43 vs :71-76); the unwritten tail is zeroed below
             if (which > 0 && D == 2) continue;
             double best = -DBL_MAX; int qb = 0x7fffffff;
+            #pragma unroll 1
             for (int q = lane; q < npt; q += TG_NL) {
                 int i0; double wq[3], b[D];
                 tg_bezier_vel_weights(q, i0, wq);
@@ -787,6 +801,7 @@ TG_FN void tg_rows_derivative(const TgLayout &L, const int *sp, const double *pa
                     if (which == 0) dsdb = bv > 0 ? b[c] / bv : 0.0;
                     else if (which == 1) dsdb = c == D - 1 ? -1.0 : 0.0;
                     else dsdb = (c < 2 && bv > 0) ? b[c] / bv : 0.0;
+                    #pragma unroll 1
                     for (int t = 0; t < 3; t++)
                         if (wq[t] != 0) row[(c * N + i0 + t) * cs] = -dsdb * wq[t] / al;
                     da += dsdb * b[c];
@@ -797,12 +812,14 @@ TG_FN void tg_rows_derivative(const TgLayout &L, const int *sp, const double *pa
         }
     }
     // acceleration control points A_j = (P_j - 2 P_{j+1} + P_{j+2}) / alpha^2 (minus gravity in 3-D), jerk J_j = D3_j / alpha^3
+    #pragma unroll 1
     for (int which = 0; which < 2; which++) {
         if (!sp[which == 0 ? TG_SP_DB_MAXA : TG_SP_DB_JERK]) continue;
         const int npt = which == 0 ? N - 2 : N - 3;
         const double grav = (which == 0 && sp[TG_SP_DB_GRAV] && D == 3) ? par[L.p_grav] : 0.0;
         const double sc = which == 0 ? 1 / (al * al) : 1 / (al * al * al);
         double best = -DBL_MAX; int qb = 0x7fffffff;
+        #pragma unroll 1
         for (int q = lane; q < npt; q += TG_NL) {
             double b[D];
 #pragma unroll
@@ -825,6 +842,7 @@ TG_FN void tg_rows_derivative(const TgLayout &L, const int *sp, const double *pa
 #pragma unroll
             for (int c = 0; c < D; c++) {
                 const double dsdb = bv > 0 ? b[c] / bv : 0.0;
+                #pragma unroll 1
                 for (int t = 0; t <= k; t++) {
                     // tg_diff order 2: +P_j -2P_{j+1} +P_{j+2}; order 3: -P_j +3P_{j+1} -3P_{j+2} +P_{j+3}
                     const double st = k == 2 ? (t == 1 ? -2.0 : 1.0) : tg_stencil(3, t);
@@ -836,6 +854,7 @@ TG_FN void tg_rows_derivative(const TgLayout &L, const int *sp, const double *pa
         }
         r++;
     }
+    #pragma unroll 1
     for (int q = r + lane; q < L.r_db + L.n_db; q += TG_NL) cv[q] = -0.0;
 }
 
@@ -849,6 +868,7 @@ TG_FN void tg_rows_tangential(const TgLayout &L, const int *sp, const double *pa
     const double al = x[L.ia];
     const double lo_lim = par[L.p_tanmin], hi_lim = par[L.p_tanmax];
     const int cs = J ? J->cs : 0;
+    #pragma unroll 1
     for (int j = lane; j < nint; j += TG_NL) {
         TgInterval<D> I;
         tg_load_interval<D>(x, N, j, I);
@@ -863,6 +883,7 @@ TG_FN void tg_rows_tangential(const TgLayout &L, const int *sp, const double *pa
         double v[D], a[D];
         tg_velocity<D>(I, 0.0, al, v); tg_acceleration<D>(I, 0.0, al, a);
         double hi = tg_dot<D>(a, v), lo = hi, thi = 0, tlo = 0;
+        #pragma unroll 1
         for (int q = 0; q < 3; q++) {
             const double t = q < 2 ? roots[q] * al : al;
             if (t < 0 || t > al) continue;
@@ -879,6 +900,7 @@ TG_FN void tg_rows_tangential(const TgLayout &L, const int *sp, const double *pa
         cv[L.r_tanu + j] = hi_lim - ymax;
         cv[L.r_tanu + nint + j] = hi_lim - ymin;
         if (J) {
+            #pragma unroll 1
             for (int e = 0; e < 2; e++) {
                 const double s = e ? lo : hi, t = e ? tlo : thi;
                 double gl[4 * D];
@@ -912,6 +934,7 @@ TG_FN void tg_rows_turning(const TgLayout &L, const int *sp, const double *par, 
     const int first = L.turn_first, nint = L.turn_ncp - 3;
     double best = 0; int jb = 0x7fffffff;
     double gbest[4 * D], gl[4 * D];
+    #pragma unroll 1
     for (int j = lane; j < nint; j += TG_NL) {
         TgInterval<D> I;
         tg_load_interval<D>(x, N, first + j, I);
@@ -945,6 +968,7 @@ template <int D>
 TG_FN void tg_rows_sfc(const TgLayout &L, const int *sp, const double *par, const double *x, double *cv)
 {
     const int N = L.N, nint = L.nint, lane = TG_LANE(), npts = 4 * nint;
+    #pragma unroll 1
     for (int q = lane; q < npts; q += TG_NL) {
         const int j = q >> 2, k = q & 3;
         const double *cor = par + L.p_sfc + tg_corridor_of_interval(sp, j) * tg_sfc_stride(D);
@@ -969,11 +993,13 @@ template <int D>
 TG_FN void tg_jac_sfc(const TgLayout &L, const int *sp, const double *par, const TgJac &J)
 {
     const int N = L.N, nint = L.nint, lane = TG_LANE(), npts = 4 * nint;
+    #pragma unroll 1
     for (int q = lane; q < npts * D; q += TG_NL) {
         const int rr = q / npts, idx = q - rr * npts;
         const int j = idx >> 2, k = idx & 3;
         const double *cor = par + L.p_sfc + tg_corridor_of_interval(sp, j) * tg_sfc_stride(D);
         double *rl = J.p + (L.r_sfcl + q) * J.rs, *ru = J.p + (L.r_sfcu + q) * J.rs;
+        #pragma unroll 1
         for (int i = 0; i < L.n; i++) { rl[i * J.cs] = 0; ru[i * J.cs] = 0; }
 #pragma unroll
         for (int c = 0; c < D; c++)
@@ -994,6 +1020,7 @@ TG_FN void tg_rows_obstacles(const TgLayout &L, const int *sp, const double *par
 {
     (void)sp;
     const int N = L.N, nint = L.nint, K = L.n_obs, lane = TG_LANE();
+    #pragma unroll 1
     for (int q = lane; q < K * nint; q += TG_NL) {
         const int i = q / nint, j = q - i * nint;
         double ctr[D];
@@ -1002,8 +1029,10 @@ TG_FN void tg_rows_obstacles(const TgLayout &L, const int *sp, const double *par
         scratch[q] = tg_hull_distance<D>(x, N, j, ctr, par[L.p_obs_r + i], 0);
     }
     TG_SYNC();
+    #pragma unroll 1
     for (int i = lane; i < K; i += TG_NL) {
         double best = DBL_MAX; int jb = 0;
+        #pragma unroll 1
         for (int j = 0; j < nint; j++)
             if (best > scratch[i * nint + j]) { best = scratch[i * nint + j]; jb = j; }
         cv[L.r_obs + i] = best;
@@ -1029,9 +1058,11 @@ TG_HD int tg_scratch_doubles(const TgLayout &L) { return L.n_obs * L.nint > 0 ? 
 TG_FN void tg_zero_nonlinear_rows(const TgLayout &L, const TgJac &J)
 {
     const int lane = TG_LANE();
+    #pragma unroll 1
     for (int r = 0; r < L.m; r++) {
         if (tg_nlrow(L, r) < 0) continue;
         double *row = tg_jrow(J, L, r);
+        #pragma unroll 1
         for (int i = lane; i < L.n; i += TG_NL) row[i * J.cs] = 0;
     }
     TG_SYNC();
@@ -1054,21 +1085,12 @@ TG_FN void tg_constraints_d(const TgLayout &L, const int *sp, const double *par,
     TG_SYNC();
 }
 
-TG_FN void tg_constraints(const TgLayout &L, const int *sp, const double *par, const double *x, double *cv,
-                          const TgJac *J, double *scratch)
-{
-    if (L.d == 2) tg_constraints_d<2>(L, sp, par, x, cv, J, scratch);
-    else tg_constraints_d<3>(L, sp, par, x, cv, J, scratch);
-}
-
 // constant Jacobian rows of the linear blocks (full-row sink only: compact == 0)
-TG_FN void tg_linear_jacobian(const TgLayout &L, const int *sp, const double *par, const TgJac &J)
+template <int D>
+TG_FN void tg_linear_jacobian_d(const TgLayout &L, const int *sp, const double *par, const TgJac &J)
 {
     tg_jac_location(L, sp, par, J);
-    if (L.n_sfc) {
-        if (L.d == 2) tg_jac_sfc<2>(L, sp, par, J);
-        else tg_jac_sfc<3>(L, sp, par, J);
-    }
+    if (L.n_sfc) tg_jac_sfc<D>(L, sp, par, J);
     TG_SYNC();
 }
 

@@ -33,41 +33,66 @@ struct TgSqpResult {
     double f;
 };
 
+// Per-problem state.  The PERSISTENT part survives between the two stages of an iteration (it lives in global
+// memory when the stages run as separate lock-step kernels); the SCRATCH part is only used inside a stage.
+struct TgSqpCtl {
+    double f, f0, t0, h3, h4, alpha, acc;
+    int state, iter, ireset, line, badlin, nfev, status, need_reset, maxiter, flags;
+};
+enum { TG_ST_INIT = 0, TG_ST_QP, TG_ST_LS, TG_ST_UPDATE, TG_ST_DONE };
+#define TG_CTL_DOUBLES ((int)((sizeof(TgSqpCtl) + 7) / 8))
+
 struct TgSqpWs {
     int n, n1, m, lda, ldq, nc;      // nc = m + 2*n1 (constraints incl. variable bounds)
-    double *x, *xl, *xu, *g, *s, *x0, *u, *v, *w, *gl;
-    double *c, *mu, *r, *cf;
-    double *A, *Lm, *Dd, *Jq, *R;
-    double *z, *dq, *rq, *np, *uq, *xq, *hw;
+    TgSqpCtl *ctl;
+    // persistent
+    double *x, *xl, *xu, *g, *s, *x0, *gl, *c, *mu, *r, *Lm, *Dd, *A;
+    // scratch
+    double *u, *v, *w, *cf, *Jq, *R, *z, *dq, *rq, *np, *uq, *xq, *hw, *scratch;
     int *act, *iact;
-    double *scratch;
 };
 
 TG_HD int tg_odd(int v) { return v | 1; }
 
-TG_HD size_t tg_sqp_carve(const TgLayout &L, double *base, TgSqpWs *W)
+// carves the two regions; returns their sizes in doubles through np_ / ns_
+TG_HD void tg_sqp_carve2(const TgLayout &L, double *pbase, double *sbase, TgSqpWs *W, size_t *np_, size_t *ns_)
 {
     const int n = L.n, n1 = n + 1, m = L.m;
-    size_t o = 0;
     TgSqpWs w;
     w.n = n; w.n1 = n1; w.m = m; w.lda = tg_odd(m > 0 ? m : 1); w.ldq = tg_odd(n1); w.nc = m + 2 * n1;
+    size_t o = 0;
+    double *base = pbase;
 #define TG_TAKE(field, count) w.field = base ? base + o : 0; o += (size_t)(count)
-    TG_TAKE(x, n1); TG_TAKE(xl, n1); TG_TAKE(xu, n1); TG_TAKE(g, n1); TG_TAKE(s, n1); TG_TAKE(x0, n1);
-    TG_TAKE(u, n1); TG_TAKE(v, n1); TG_TAKE(w, n1); TG_TAKE(gl, n1);
-    TG_TAKE(c, m + 1); TG_TAKE(mu, m + 1); TG_TAKE(r, w.nc + 1); TG_TAKE(cf, m + 1);
+    w.ctl = (TgSqpCtl *)base; o += TG_CTL_DOUBLES;
+    TG_TAKE(x, n1); TG_TAKE(xl, n1); TG_TAKE(xu, n1); TG_TAKE(g, n1); TG_TAKE(s, n1); TG_TAKE(x0, n1); TG_TAKE(gl, n1);
+    TG_TAKE(c, m + 1); TG_TAKE(mu, m + 1); TG_TAKE(r, w.nc + 1);
     TG_TAKE(Lm, n * n); TG_TAKE(Dd, n1);
+    TG_TAKE(A, w.lda * n1);
+    if (np_) *np_ = o;
+    o = 0; base = sbase;
+    TG_TAKE(u, n1); TG_TAKE(v, n1); TG_TAKE(w, n1); TG_TAKE(cf, m + 1);
     TG_TAKE(Jq, w.ldq * n1); TG_TAKE(R, w.ldq * n1);
     TG_TAKE(z, n1); TG_TAKE(dq, n1); TG_TAKE(rq, n1); TG_TAKE(np, n1); TG_TAKE(uq, n1 + 1); TG_TAKE(xq, n1); TG_TAKE(hw, n1);
     TG_TAKE(scratch, tg_scratch_doubles(L));
     double *ints = base ? base + o : 0; o += (size_t)((n1 + 1 + w.nc + 1) / 2 + 1);
     w.act = (int *)ints; w.iact = w.act + n1 + 1;
-    TG_TAKE(A, w.lda * n1);
 #undef TG_TAKE
+    if (ns_) *ns_ = o;
     if (W) *W = w;
-    return o;
 }
 
-TG_HD size_t tg_sqp_workspace_doubles(const TgLayout &L) { return tg_sqp_carve(L, 0, 0); }
+TG_HD size_t tg_sqp_persistent_doubles(const TgLayout &L) { size_t a, b; tg_sqp_carve2(L, 0, 0, 0, &a, &b); return a; }
+TG_HD size_t tg_sqp_scratch_doubles(const TgLayout &L) { size_t a, b; tg_sqp_carve2(L, 0, 0, 0, &a, &b); return b; }
+TG_HD size_t tg_sqp_workspace_doubles(const TgLayout &L) { return tg_sqp_persistent_doubles(L) + tg_sqp_scratch_doubles(L); }
+
+// one contiguous buffer: persistent part first, scratch behind it
+TG_HD size_t tg_sqp_carve(const TgLayout &L, double *base, TgSqpWs *W)
+{
+    const size_t np_ = tg_sqp_persistent_doubles(L);
+    size_t a, b;
+    tg_sqp_carve2(L, base, base ? base + np_ : 0, W, &a, &b);
+    return a + b;
+}
 
 TG_HD bool tg_finite(double v) { return v - v == 0; }
 
@@ -82,16 +107,20 @@ TG_FN void tg_ldl_update(int n, double sigma, double *z, double *Lm, double *Dd,
     if (sigma == 0) return;
     double t = 1 / sigma;
     if (sigma < 0) {
+        #pragma unroll 1
         for (int i = lane; i < n; i += TG_NL) w[i] = z[i];
         TG_SYNC();
+        #pragma unroll 1
         for (int i = 0; i < n; i++) {
             const double vv = w[i];
             t += vv * vv / Dd[i];
+            #pragma unroll 1
             for (int j = i + 1 + lane; j < n; j += TG_NL) w[j] -= vv * Lm[i * n + j];
             TG_SYNC();
         }
         if (t >= 0) t = DBL_EPSILON / sigma;
         if (lane == 0) {
+            #pragma unroll 1
             for (int i = n - 1; i >= 0; i--) {
                 const double uu = w[i];
                 w[i] = t;
@@ -101,6 +130,7 @@ TG_FN void tg_ldl_update(int n, double sigma, double *z, double *Lm, double *Dd,
         t = tg_bcast(t, 0);
         TG_SYNC();
     }
+    #pragma unroll 1
     for (int i = 0; i < n; i++) {
         const double vv = z[i], di = Dd[i];
         const double delta = vv / di;
@@ -112,12 +142,14 @@ TG_FN void tg_ldl_update(int n, double sigma, double *z, double *Lm, double *Dd,
         const double beta = delta / tp;
         if (alpha > 4) {
             const double gamma = t / tp;
+            #pragma unroll 1
             for (int j = i + 1 + lane; j < n; j += TG_NL) {
                 const double uu = Lm[i * n + j];
                 Lm[i * n + j] = gamma * uu + beta * z[j];
                 z[j] -= vv * uu;
             }
         } else {
+            #pragma unroll 1
             for (int j = i + 1 + lane; j < n; j += TG_NL) {
                 z[j] -= vv * Lm[i * n + j];
                 Lm[i * n + j] += beta * z[j];
@@ -133,14 +165,18 @@ TG_FN void tg_ldl_update(int n, double sigma, double *z, double *Lm, double *Dd,
 TG_FN void tg_ldl_apply(int n, const double *Lm, const double *Dd, const double *s, double *tmp, double *out)
 {
     const int lane = TG_LANE();
+    #pragma unroll 1
     for (int i = lane; i < n; i += TG_NL) {
         double h = s[i];
+        #pragma unroll 1
         for (int j = i + 1; j < n; j++) h += Lm[i * n + j] * s[j];
         tmp[i] = Dd[i] * h;
     }
     TG_SYNC();
+    #pragma unroll 1
     for (int i = lane; i < n; i += TG_NL) {
         double h = tmp[i];
+        #pragma unroll 1
         for (int j = 0; j < i; j++) h += Lm[j * n + i] * tmp[j];
         out[i] = h;
     }
@@ -161,11 +197,13 @@ TG_HD void tg_qp_normal(const TgSqpWs &W, int nq, int p, double *np)
 {
     const int lane = TG_LANE();
     if (p < W.m) {
+        #pragma unroll 1
         for (int i = lane; i < nq; i += TG_NL) np[i] = W.A[i * W.lda + p];
     } else {
         const int q = p - W.m;
         const int i0 = q < W.n1 ? q : q - W.n1;
         const double sg = q < W.n1 ? 1.0 : -1.0;
+        #pragma unroll 1
         for (int i = lane; i < nq; i += TG_NL) np[i] = i == i0 ? sg : 0.0;
     }
     TG_SYNC();
@@ -176,6 +214,7 @@ TG_HD double tg_qp_value(const TgSqpWs &W, int nq, int p)
 {
     if (p < W.m) {
         double s = 0;
+        #pragma unroll 1
         for (int i = TG_LANE(); i < nq; i += TG_NL) s += W.A[i * W.lda + p] * W.xq[i];
         return tg_wsum(s) + W.c[p];
     }
@@ -188,9 +227,11 @@ TG_FN void tg_qp_directions(const TgSqpWs &W, int nq, int iq, double &d2n, doubl
 {
     const int lane = TG_LANE(), ld = W.ldq;
     double a = 0, b = 0;
+    #pragma unroll 1
     for (int k = lane; k < nq; k += TG_NL) {
         double h = 0;
         const double *col = W.Jq + k * ld;
+        #pragma unroll 1
         for (int i = 0; i < nq; i++) h += col[i] * W.np[i];
         W.dq[k] = h;
         W.hw[k] = h;
@@ -200,16 +241,20 @@ TG_FN void tg_qp_directions(const TgSqpWs &W, int nq, int iq, double &d2n, doubl
     d2n = tg_wsum(a);
     dn = tg_wsum(b);
     TG_SYNC();
+    #pragma unroll 1
     for (int i = lane; i < nq; i += TG_NL) {
         double h = 0;
+        #pragma unroll 1
         for (int k = iq; k < nq; k++) h += W.Jq[k * ld + i] * W.dq[k];
         W.z[i] = h;
     }
     // back substitution R rq = d1 (column oriented; hw holds the running right-hand side)
+    #pragma unroll 1
     for (int j = iq - 1; j >= 0; j--) {
         const double rj = W.hw[j] / W.R[j * ld + j];
         TG_SYNC();
         if (lane == 0) W.rq[j] = rj;
+        #pragma unroll 1
         for (int k = lane; k < j; k += TG_NL) W.hw[k] -= W.R[j * ld + k] * rj;
         TG_SYNC();
     }
@@ -221,6 +266,7 @@ TG_FN void tg_qp_add(const TgSqpWs &W, int nq, int iq)
 {
     const int lane = TG_LANE(), ld = W.ldq;
     double nn = 0;
+    #pragma unroll 1
     for (int k = iq + lane; k < nq; k += TG_NL) nn += W.dq[k] * W.dq[k];
     nn = tg_wsum(nn);
     const double d0 = W.dq[iq];
@@ -229,13 +275,17 @@ TG_FN void tg_qp_add(const TgSqpWs &W, int nq, int iq)
     const double ww = 2 * (nn - sigma * d0);
     TG_SYNC();
     if (ww > 0) {
+        #pragma unroll 1
         for (int i = lane; i < nq; i += TG_NL) {
             double t = 0;
+            #pragma unroll 1
             for (int k = iq; k < nq; k++) t += W.Jq[k * ld + i] * (k == iq ? d0 - sigma : W.dq[k]);
             t *= 2 / ww;
+            #pragma unroll 1
             for (int k = iq; k < nq; k++) W.Jq[k * ld + i] -= t * (k == iq ? d0 - sigma : W.dq[k]);
         }
     }
+    #pragma unroll 1
     for (int k = lane; k < iq; k += TG_NL) W.R[iq * ld + k] = W.dq[k];
     if (lane == 0) W.R[iq * ld + iq] = ww > 0 ? sigma : d0;
     TG_SYNC();
@@ -246,12 +296,15 @@ TG_FN void tg_qp_drop(const TgSqpWs &W, int nq, int &iq, int l)
 {
     const int lane = TG_LANE(), ld = W.ldq;
     if (lane == 0) W.iact[W.act[l]] = 0;
+    #pragma unroll 1
     for (int k = l; k < iq - 1; k++) {
+        #pragma unroll 1
         for (int i = lane; i <= k + 1; i += TG_NL) W.R[k * ld + i] = W.R[(k + 1) * ld + i];
         if (lane == 0) { W.act[k] = W.act[k + 1]; W.uq[k] = W.uq[k + 1]; }
         TG_SYNC();
     }
     iq--;
+    #pragma unroll 1
     for (int j = l; j < iq; j++) {
         double cc = W.R[j * ld + j], ss = W.R[j * ld + j + 1];
         const double h = sqrt(cc * cc + ss * ss);
@@ -259,11 +312,13 @@ TG_FN void tg_qp_drop(const TgSqpWs &W, int nq, int &iq, int l)
         if (h == 0) continue;
         cc /= h; ss /= h;
         if (lane == 0) { W.R[j * ld + j] = h; W.R[j * ld + j + 1] = 0; }
+        #pragma unroll 1
         for (int k = j + 1 + lane; k < iq; k += TG_NL) {
             const double t1 = W.R[k * ld + j], t2 = W.R[k * ld + j + 1];
             W.R[k * ld + j] = cc * t1 + ss * t2;
             W.R[k * ld + j + 1] = -ss * t1 + cc * t2;
         }
+        #pragma unroll 1
         for (int i = lane; i < nq; i += TG_NL) {
             const double t1 = W.Jq[j * ld + i], t2 = W.Jq[(j + 1) * ld + i];
             W.Jq[j * ld + i] = cc * t1 + ss * t2;
@@ -280,31 +335,41 @@ TG_FN int tg_qp_solve(const TgSqpWs &W, int nq, int meq, double rho)
     const int nc = m + 2 * W.n1;
     const double EPS_DEP = 1e-26;     // |d2|^2 <= EPS_DEP |d|^2 : normal lies in the span of the active ones
     // ---- J = L^-T D^-1/2 (upper triangular), augmented entry 1/sqrt(rho)
+    #pragma unroll 1
     for (int k = lane; k < nq; k += TG_NL) {
         double *col = W.Jq + k * ld;
+        #pragma unroll 1
         for (int i = 0; i < nq; i++) col[i] = 0;
         if (k < n) {
             col[k] = 1;
+            #pragma unroll 1
             for (int i = k - 1; i >= 0; i--) {
                 double h = 0;
+                #pragma unroll 1
                 for (int j = i + 1; j <= k; j++) h += W.Lm[i * n + j] * col[j];
                 col[i] = -h;
             }
             const double sc = 1 / sqrt(W.Dd[k]);
+            #pragma unroll 1
             for (int i = 0; i <= k; i++) col[i] *= sc;
         } else col[k] = 1 / rho;      // SLSQP's LSQ puts rho itself (not its root) on the diagonal of E: penalty rho^2/2 delta^2
     }
+    #pragma unroll 1
     for (int p = lane; p < nc; p += TG_NL) { W.iact[p] = 0; W.r[p] = 0; }
     TG_SYNC();
     // ---- unconstrained minimiser xq = -J J' g
+    #pragma unroll 1
     for (int k = lane; k < nq; k += TG_NL) {
         double h = 0;
+        #pragma unroll 1
         for (int i = 0; i < nq; i++) h += W.Jq[k * ld + i] * W.g[i];
         W.dq[k] = h;
     }
     TG_SYNC();
+    #pragma unroll 1
     for (int i = lane; i < nq; i += TG_NL) {
         double h = 0;
+        #pragma unroll 1
         for (int k = 0; k < nq; k++) h += W.Jq[k * ld + i] * W.dq[k];
         W.xq[i] = -h;
     }
@@ -312,13 +377,16 @@ TG_FN int tg_qp_solve(const TgSqpWs &W, int nq, int meq, double rho)
     int iq = 0;
     double d2n, dn;
     // ---- equality rows, in order
+    #pragma unroll 1
     for (int p = 0; p < meq; p++) {
         tg_qp_normal(W, nq, p, W.np);
         tg_qp_directions(W, nq, iq, d2n, dn);
         if (!(d2n > EPS_DEP * dn)) return 6;
         const double sv = tg_qp_value(W, nq, p);
         const double t2 = -sv / d2n;
+        #pragma unroll 1
         for (int i = lane; i < nq; i += TG_NL) W.xq[i] += t2 * W.z[i];
+        #pragma unroll 1
         for (int k = lane; k < iq; k += TG_NL) W.uq[k] -= t2 * W.rq[k];
         if (lane == 0) { W.uq[iq] = t2; W.act[iq] = p; W.iact[p] = 1; }
         TG_SYNC();
@@ -327,14 +395,17 @@ TG_FN int tg_qp_solve(const TgSqpWs &W, int nq, int meq, double rho)
     }
     // ---- inequality rows and bounds
     const int itmax = 10 * (nc + nq) + 100;
+    #pragma unroll 1
     for (int it = 0; it < itmax; it++) {
         // most violated inactive constraint
         double best = 0; int ip = 0x7fffffff;
+        #pragma unroll 1
         for (int p = meq + lane; p < nc; p += TG_NL) {
             if (W.iact[p]) continue;
             double sv, tol;
             if (p < m) {
                 double h = 0, sc = fabs(W.c[p]);
+                #pragma unroll 1
                 for (int i = 0; i < nq; i++) { const double t = W.A[i * W.lda + p] * W.xq[i]; h += t; sc += fabs(t); }
                 sv = h + W.c[p];
                 tol = 1e-13 * sc;
@@ -351,6 +422,7 @@ TG_FN int tg_qp_solve(const TgSqpWs &W, int nq, int meq, double rho)
         }
         tg_wargmin(best, ip);
         if (ip == 0x7fffffff) {
+            #pragma unroll 1
             for (int k = lane; k < iq; k += TG_NL) W.r[W.act[k]] = W.uq[k];
             TG_SYNC();
             return TG_QP_OK;
@@ -358,10 +430,12 @@ TG_FN int tg_qp_solve(const TgSqpWs &W, int nq, int meq, double rho)
         tg_qp_normal(W, nq, ip, W.np);
         double uip = 0;
         double sv = tg_qp_value(W, nq, ip);
+        #pragma unroll 1
         for (int inner = 0; inner < itmax; inner++) {
             tg_qp_directions(W, nq, iq, d2n, dn);
             // dual step length: active inequalities whose multiplier would turn negative
             double t1 = INFINITY; int l = 0x7fffffff;
+            #pragma unroll 1
             for (int k = lane; k < iq; k += TG_NL)
                 if (W.act[k] >= meq && W.rq[k] > 0) {
                     const double t = W.uq[k] / W.rq[k];
@@ -371,6 +445,7 @@ TG_FN int tg_qp_solve(const TgSqpWs &W, int nq, int meq, double rho)
             const double t2 = d2n > EPS_DEP * dn ? -sv / d2n : INFINITY;
             const double t = t1 < t2 ? t1 : t2;
             if (!(t < INFINITY)) return 4;
+            #pragma unroll 1
             for (int k = lane; k < iq; k += TG_NL) W.uq[k] -= t * W.rq[k];
             uip += t;
             if (!(t2 < INFINITY)) {
@@ -378,6 +453,7 @@ TG_FN int tg_qp_solve(const TgSqpWs &W, int nq, int meq, double rho)
                 tg_qp_drop(W, nq, iq, l);
                 continue;
             }
+            #pragma unroll 1
             for (int i = lane; i < nq; i += TG_NL) W.xq[i] += t * W.z[i];
             TG_SYNC();
             if (t2 <= t1) {
@@ -399,6 +475,7 @@ TG_FN int tg_qp_solve(const TgSqpWs &W, int nq, int meq, double rho)
 TG_HD double tg_violation(const TgSqpWs &W, int meq, const double *weights)
 {
     double h = 0;
+    #pragma unroll 1
     for (int j = TG_LANE(); j < W.m; j += TG_NL) {
         const double cj = W.c[j];
         const double viol = j < meq ? fmax(-cj, cj) : fmax(-cj, 0.0);
@@ -411,11 +488,12 @@ TG_HD double tg_violation(const TgSqpWs &W, int meq, const double *weights)
 #define TG_FD_STEP 1.4901161193847656e-08     // scipy/optimize/_slsqp_py.py:34
 
 // objective and constraints at W.x; with derivs also g and the nonlinear rows of A (analytic)
+template <int D>
 TG_FN double tg_sqp_evaluate(const TgLayout &L, const int *sp, const double *par, const TgSqpWs &W, bool derivs)
 {
     const double f = tg_objective(L, sp, W.x, derivs ? W.g : 0);
     TgJac sink = {W.A, 1, W.lda, 0};
-    tg_constraints(L, sp, par, W.x, W.c, derivs ? &sink : 0, W.scratch);
+    tg_constraints_d<D>(L, sp, par, W.x, W.c, derivs ? &sink : 0, W.scratch);
     TG_SYNC();
     return f;
 }
@@ -424,9 +502,11 @@ TG_FN double tg_sqp_evaluate(const TgLayout &L, const int *sp, const double *par
 // abs_step=eps, bounds) on the objective and on every nonlinear constraint
 // (scipy/optimize/_slsqp_py.py:353-366, _numdiff.py); linear rows keep their constant A.
 // Requires f, W.c at W.x.  n extra evaluations.
+template <int D>
 TG_FN void tg_sqp_fd_derivatives(const TgLayout &L, const int *sp, const double *par, const TgSqpWs &W, double f)
 {
     const int lane = TG_LANE(), n = L.n, m = L.m;
+    #pragma unroll 1
     for (int i = 0; i < n; i++) {
         const double xi = W.x[i], lo = W.xl[i], hi = W.xu[i];
         double h = TG_FD_STEP;
@@ -441,212 +521,271 @@ TG_FN void tg_sqp_fd_derivatives(const TgLayout &L, const int *sp, const double 
         TG_SYNC();
         const double dx = W.x[i] - xi;
         const double f1 = tg_objective(L, sp, W.x, 0);
-        tg_constraints(L, sp, par, W.x, W.cf, 0, W.scratch);
+        tg_constraints_d<D>(L, sp, par, W.x, W.cf, 0, W.scratch);
         TG_SYNC();
         if (lane == 0) { W.g[i] = (f1 - f) / dx; W.x[i] = xi; }
+        #pragma unroll 1
         for (int j = lane; j < m; j += TG_NL)
             if (tg_nlrow(L, j) >= 0) W.A[i * W.lda + j] = (W.cf[j] - W.c[j]) / dx;
         TG_SYNC();
     }
 }
 
-// trace (host tests only): per major iteration [f, alpha, x...]
-TG_FN void tg_sqp_solve(const TgLayout &L, const int *sp, const double *par, double *xio, double *wsbase, int maxiter,
-                        double acc, int flags, TgSqpResult *res, double *trace, int trace_cap)
+// ---------------------------------------------------------------------------
+// The iteration, split into two stages so that it can run either fused (one warp loops over both stages
+// until its problem is done) or in lock step (all problems run stage LS, then all run stage QP, ... as
+// separate kernels: every warp of the machine then executes the same, small piece of code at the same time).
+//   stage LS : evaluation at the starting point / the whole line search on the L1 merit function
+//   stage QP : convergence test after the step, damped BFGS update, next QP subproblem, merit set-up
+// ---------------------------------------------------------------------------
+TG_FN void tg_sqp_begin(const TgLayout &L, const TgSqpWs &W, const double *xin, int maxiter, double acc, int flags)
 {
-    TgSqpWs W;
-    tg_sqp_carve(L, wsbase, &W);
-    const int lane = TG_LANE(), n = L.n, m = L.m, meq = L.meq, n1 = W.n1;
-    const double tol = 10 * acc;
-    const bool fd = (flags & TG_SQP_FD_JACOBIAN) != 0;
-    // ---- variables and bounds (TG/objectives/objective_variables.py:50-61); x0 clipped as scipy does
+    const int lane = TG_LANE(), n = L.n, m = L.m, n1 = W.n1;
+    // variables and bounds (TG/objectives/objective_variables.py:50-61); x0 clipped as scipy does
+    #pragma unroll 1
     for (int i = lane; i < n1; i += TG_NL) {
         double lo = -INFINITY, hi = INFINITY;
         if (i >= L.ia && i < L.it0) lo = 10e-8;
         if (i >= L.it0 && i < n) { lo = 0; hi = L.N - 3; }
         W.xl[i] = lo; W.xu[i] = hi;
-        double xv = i < n ? xio[i] : 0.0;
+        double xv = i < n ? xin[i] : 0.0;
         if (i < n) { xv = xv < lo ? lo : xv; xv = xv > hi ? hi : xv; }
-        W.x[i] = xv; W.s[i] = 0; W.g[i] = 0;
+        W.x[i] = xv; W.s[i] = 0; W.g[i] = 0; W.x0[i] = xv; W.gl[i] = 0;
     }
+    #pragma unroll 1
     for (int j = lane; j < m; j += TG_NL) W.mu[j] = 0;
+    #pragma unroll 1
     for (int q = lane; q < W.lda * n1; q += TG_NL) W.A[q] = 0;
-    TG_SYNC();
-    {
-        TgJac sink = {W.A, 1, W.lda, 0};
-        tg_linear_jacobian(L, sp, par, sink);
+    if (lane == 0) {
+        TgSqpCtl c;
+        c.f = 0; c.f0 = 0; c.t0 = 0; c.h3 = 0; c.h4 = 1; c.alpha = 1; c.acc = acc;
+        c.state = TG_ST_INIT; c.iter = 0; c.ireset = 0; c.line = 0; c.badlin = 0; c.nfev = 0; c.status = -1;
+        c.need_reset = 1; c.maxiter = maxiter; c.flags = flags;
+        *W.ctl = c;
     }
-    double f = tg_sqp_evaluate(L, sp, par, W, !fd);
-    if (fd) tg_sqp_fd_derivatives(L, sp, par, W, f);
-    int nfev = 1, iter = 0, ireset = 0, status = -1;
-    double f0 = f, h1, h2, h3, h4, t0, gs;
-    bool badlin = false;
-    bool need_reset = true;
-    for (;;) {
-        if (need_reset) {
-            // ---- reset the BFGS factor to the identity
-            ireset++;
-            if (ireset > 5) {
-                // relaxed convergence test after a positive directional derivative
-                double sn = 0;
-                for (int i = lane; i < n; i += TG_NL) sn += W.s[i] * W.s[i];
-                sn = sqrt(tg_wsum(sn));
-                h3 = tg_violation(W, meq, 0);
-                status = ((fabs(f - f0) < tol || sn < tol) && h3 < tol && !badlin && f == f) ? 0 : 8;
-                break;
-            }
-            for (int q = lane; q < n * n; q += TG_NL) W.Lm[q] = 0;
-            for (int i = lane; i < n1; i += TG_NL) W.Dd[i] = 1;
+    TG_SYNC();
+}
+
+template <int D>
+TG_FN void tg_sqp_stage_ls(const TgLayout &L, const int *sp, const double *par, const TgSqpWs &W, double *trace,
+                           int trace_cap)
+{
+    const int lane = TG_LANE(), n = L.n, meq = L.meq;
+    TgSqpCtl ctl = *W.ctl;
+    const bool fd = (ctl.flags & TG_SQP_FD_JACOBIAN) != 0;
+    if (ctl.state == TG_ST_INIT) {
+        TgJac sink = {W.A, 1, W.lda, 0};
+        tg_linear_jacobian_d<D>(L, sp, par, sink);
+        ctl.f = tg_sqp_evaluate<D>(L, sp, par, W, !fd);
+        ctl.nfev = 1;
+        if (fd) { tg_sqp_fd_derivatives<D>(L, sp, par, W, ctl.f); ctl.nfev += n; }
+        ctl.state = TG_ST_QP;
+    } else if (ctl.state == TG_ST_LS) {
+        double f;
+        for (;;) {
+            f = tg_sqp_evaluate<D>(L, sp, par, W, !fd);
+            ctl.nfev++;
+            const double t = f + tg_violation(W, meq, W.mu);
+            const double h1 = t - ctl.t0;
+            if (h1 <= ctl.h3 / 10 || ctl.line > 10) break;
+            ctl.alpha = fmax(ctl.h3 / (2 * (ctl.h3 - h1)), 0.1);
+            ctl.line++;
+            ctl.h3 = ctl.alpha * ctl.h3;
             TG_SYNC();
-            need_reset = false;
-        }
-        // ---- major iteration
-        iter++;
-        if (iter > maxiter) { status = 9; break; }
-        for (int i = lane; i < n; i += TG_NL) { W.u[i] = W.xl[i] - W.x[i]; W.v[i] = W.xu[i] - W.x[i]; }
-        TG_SYNC();
-        h4 = 1;
-#ifdef TG_DEBUG_KKT
-        if (getenv("TG_DUMP_ITER") && atoi(getenv("TG_DUMP_ITER")) == iter) {
-            FILE *fp = fopen("/tmp/qp_dump.txt", "w");
-            fprintf(fp, "%d %d %d\n", n, m, meq);
-            for (int i = 0; i < n; i++) fprintf(fp, "%.17g ", W.g[i]); fprintf(fp, "\n");
-            for (int j = 0; j < m; j++) fprintf(fp, "%.17g ", W.c[j]); fprintf(fp, "\n");
-            for (int j = 0; j < m; j++) { for (int i = 0; i < n; i++) fprintf(fp, "%.17g ", W.A[i * W.lda + j]); fprintf(fp, "\n"); }
-            for (int i = 0; i < n; i++) fprintf(fp, "%.17g ", W.u[i]); fprintf(fp, "\n");
-            for (int i = 0; i < n; i++) fprintf(fp, "%.17g ", W.v[i]); fprintf(fp, "\n");
-            for (int i = 0; i < n; i++) fprintf(fp, "%.17g ", W.Dd[i]); fprintf(fp, "\n");
-            for (int i = 0; i < n; i++) { for (int j = 0; j < n; j++) fprintf(fp, "%.17g ", j > i ? W.Lm[i * n + j] : (i == j ? 1.0 : 0.0)); fprintf(fp, "\n"); }
-            fclose(fp);
-        }
-#endif
-        int mode = tg_qp_solve(W, n, meq, 0.0);
-        badlin = false;
-        if (mode == 6 && n == meq) mode = 4;
-        if (mode == 4) {
-            // ---- augmented problem for an inconsistent linearisation
-            badlin = true;
-            for (int j = lane; j < m; j += TG_NL) W.A[n * W.lda + j] = j < meq ? -W.c[j] : fmax(-W.c[j], 0.0);
-            if (lane == 0) { W.g[n] = 0; W.u[n] = 0; W.v[n] = 1; }
-            TG_SYNC();
-            double rho = 100;
-            for (int incons = 0;; incons++) {
-                mode = tg_qp_solve(W, n1, meq, rho);
-                if (mode != 4) break;
-                rho *= 10;
-                if (incons + 1 > 5) break;
-            }
-            if (mode != TG_QP_OK) { status = mode; break; }
-            h4 = 1 - W.xq[n];
-        } else if (mode != TG_QP_OK) { status = mode; break; }
-#ifdef TG_DEBUG_KKT
-        {
-            // host-only diagnostics: KKT residual of the QP solution
-            double v[64]; tg_ldl_apply(n, W.Lm, W.Dd, W.xq, W.w, v);
-            double rs = 0, feas = 0, comp = 0, mneg = 0;
-            for (int i = 0; i < n; i++) {
-                double h = v[i] + W.g[i];
-                for (int j = 0; j < m; j++) h -= W.A[i * W.lda + j] * W.r[j];
-                h -= W.r[m + i]; h += W.r[m + n1 + i];
-                rs = fmax(rs, fabs(h));
-            }
-            for (int j = 0; j < m; j++) {
-                double h = W.c[j];
-                for (int i = 0; i < n; i++) h += W.A[i * W.lda + j] * W.xq[i];
-                if (j < meq) feas = fmax(feas, fabs(h)); else { feas = fmax(feas, -h); comp = fmax(comp, fabs(h * W.r[j])); mneg = fmin(mneg, W.r[j]); }
-            }
-            double dmin = 1e300, dmax = 0; for (int i = 0; i < n; i++) { dmin = fmin(dmin, W.Dd[i]); dmax = fmax(dmax, W.Dd[i]); }
-            double gn = 0, sn_ = 0; for (int i = 0; i < n; i++) { gn = fmax(gn, fabs(W.g[i])); sn_ = fmax(sn_, fabs(W.xq[i])); }
-            printf("  [kkt] iter %d mode %d badlin %d stat %.2e feas %.2e comp %.2e minmult %.2e f %.10g Dmin %.2e Dmax %.2e |g| %.2e |s| %.2e delta %.3g\n", iter, mode, (int)badlin, rs, feas, comp, mneg, f, dmin, dmax, gn, sn_, badlin ? W.xq[n] : 0.0);
-        }
-#endif
-        // ---- gradient of the Lagrangian at the old point, merit weights
-        for (int i = lane; i < n; i += TG_NL) {
-            double h = W.g[i];
-            for (int j = 0; j < m; j++) h -= W.A[i * W.lda + j] * W.r[j];
-            W.gl[i] = h;
-            W.s[i] = W.xq[i];
-            W.x0[i] = W.x[i];
-        }
-        f0 = f;
-        TG_SYNC();
-        gs = 0;
-        for (int i = lane; i < n; i += TG_NL) gs += W.g[i] * W.s[i];
-        gs = tg_wsum(gs);
-        h1 = 0; h2 = 0;
-        for (int j = lane; j < m; j += TG_NL) {
-            const double cj = W.c[j];
-            h2 += fmax(-cj, j < meq ? cj : 0.0);
-            const double ar = fabs(W.r[j]);
-            W.mu[j] = fmax(ar, (W.mu[j] + ar) / 2);
-            h1 += ar * fabs(cj);
-        }
-        h1 = fabs(gs) + tg_wsum(h1);
-        h2 = tg_wsum(h2);
-        TG_SYNC();
-        if (h1 < acc && h2 < acc && !badlin && f == f) { status = 0; break; }
-        h1 = tg_violation(W, meq, W.mu);
-        t0 = f + h1;
-        h3 = gs - h1 * h4;
-        if (h3 >= 0) { need_reset = true; continue; }
-        // ---- line search on the L1 merit function
-        double alpha = 1;
-        for (int line = 1;; line++) {
-            h3 = alpha * h3;
+            #pragma unroll 1
             for (int i = lane; i < n; i += TG_NL) {
-                W.s[i] *= alpha;
+                W.s[i] *= ctl.alpha;
                 double xv = W.x0[i] + W.s[i];
                 xv = xv < W.xl[i] ? W.xl[i] : xv;
                 xv = xv > W.xu[i] ? W.xu[i] : xv;
                 W.x[i] = xv;
             }
             TG_SYNC();
-            f = tg_sqp_evaluate(L, sp, par, W, !fd);
-            nfev++;
-            const double t = f + tg_violation(W, meq, W.mu);
-            h1 = t - t0;
-            if (h1 <= h3 / 10 || line > 10) break;
-            alpha = fmax(h3 / (2 * (h3 - h1)), 0.1);
         }
-        if (trace && lane == 0 && (iter * (n + 2) <= trace_cap)) {
-            double *tr = trace + (iter - 1) * (n + 2);
-            tr[0] = f; tr[1] = alpha;
+        ctl.f = f;
+        if (trace && lane == 0 && (ctl.iter * (n + 2) <= trace_cap)) {
+            double *tr = trace + (ctl.iter - 1) * (n + 2);
+            tr[0] = f; tr[1] = ctl.alpha;
             for (int i = 0; i < n; i++) tr[2 + i] = W.x[i];
         }
-        // ---- convergence test after the step
-        {
-            double sn = 0;
-            for (int i = lane; i < n; i += TG_NL) sn += W.s[i] * W.s[i];
-            sn = sqrt(tg_wsum(sn));
-            h3 = tg_violation(W, meq, 0);
-            if ((fabs(f - f0) < acc || sn < acc) && h3 < acc && !badlin && f == f) { status = 0; break; }
-        }
-        // ---- damped BFGS update of L D L' (analytic derivatives at the new point are already in g, A)
-        if (fd) { tg_sqp_fd_derivatives(L, sp, par, W, f); nfev += n; }
-        for (int i = lane; i < n; i += TG_NL) {
-            double h = W.g[i];
-            for (int j = 0; j < m; j++) h -= W.A[i * W.lda + j] * W.r[j];
-            W.u[i] = h - W.gl[i];
-        }
-        TG_SYNC();
-        tg_ldl_apply(n, W.Lm, W.Dd, W.s, W.w, W.v);
-        h1 = 0; h2 = 0;
-        for (int i = lane; i < n; i += TG_NL) { h1 += W.s[i] * W.u[i]; h2 += W.s[i] * W.v[i]; }
-        h1 = tg_wsum(h1); h2 = tg_wsum(h2);
-        h3 = 0.2 * h2;
-        if (h1 < h3) {
-            h4 = (h2 - h3) / (h2 - h1);
-            h1 = h3;
-            for (int i = lane; i < n; i += TG_NL) W.u[i] = h4 * W.u[i] + (1 - h4) * W.v[i];
-        }
-        TG_SYNC();
-        if (h1 == 0 || h2 == 0) { need_reset = true; continue; }
-        tg_ldl_update(n, 1 / h1, W.u, W.Lm, W.Dd, W.w);
-        tg_ldl_update(n, -1 / h2, W.v, W.Lm, W.Dd, W.w);
+        // scipy differentiates at the accepted point (mode -1); harmless extra work if the next test ends the run
+        if (fd) { tg_sqp_fd_derivatives<D>(L, sp, par, W, f); ctl.nfev += n; }
+        ctl.state = TG_ST_UPDATE;
     }
-    for (int i = lane; i < n; i += TG_NL) xio[i] = W.x[i];
     TG_SYNC();
-    if (res && lane == 0) { res->status = status; res->nit = iter > maxiter ? maxiter : iter; res->nfev = nfev; res->f = f; }
+    if (lane == 0) *W.ctl = ctl;
+    TG_SYNC();
+}
+
+TG_FN void tg_sqp_stage_qp(const TgLayout &L, const TgSqpWs &W)
+{
+    const int lane = TG_LANE(), n = L.n, m = L.m, meq = L.meq, n1 = W.n1;
+    TgSqpCtl ctl = *W.ctl;
+    const double acc = ctl.acc, tol = 10 * ctl.acc;
+    double h1, h2, h3;
+    if (ctl.state == TG_ST_UPDATE) {
+        // ---- convergence test after the step
+        double sn = 0;
+        #pragma unroll 1
+        for (int i = lane; i < n; i += TG_NL) sn += W.s[i] * W.s[i];
+        sn = sqrt(tg_wsum(sn));
+        h3 = tg_violation(W, meq, 0);
+        if ((fabs(ctl.f - ctl.f0) < acc || sn < acc) && h3 < acc && !ctl.badlin && ctl.f == ctl.f) {
+            ctl.status = 0; ctl.state = TG_ST_DONE;
+        } else {
+            // ---- damped BFGS update of L D L' (derivatives at the new point are already in g, A)
+            #pragma unroll 1
+            for (int i = lane; i < n; i += TG_NL) {
+                double h = W.g[i];
+                #pragma unroll 1
+                for (int j = 0; j < m; j++) h -= W.A[i * W.lda + j] * W.r[j];
+                W.u[i] = h - W.gl[i];
+            }
+            TG_SYNC();
+            tg_ldl_apply(n, W.Lm, W.Dd, W.s, W.w, W.v);
+            h1 = 0; h2 = 0;
+            #pragma unroll 1
+            for (int i = lane; i < n; i += TG_NL) { h1 += W.s[i] * W.u[i]; h2 += W.s[i] * W.v[i]; }
+            h1 = tg_wsum(h1); h2 = tg_wsum(h2);
+            h3 = 0.2 * h2;
+            if (h1 < h3) {
+                const double h4 = (h2 - h3) / (h2 - h1);
+                h1 = h3;
+                #pragma unroll 1
+                for (int i = lane; i < n; i += TG_NL) W.u[i] = h4 * W.u[i] + (1 - h4) * W.v[i];
+            }
+            TG_SYNC();
+            if (h1 == 0 || h2 == 0) ctl.need_reset = 1;
+            else {
+                tg_ldl_update(n, 1 / h1, W.u, W.Lm, W.Dd, W.w);
+                tg_ldl_update(n, -1 / h2, W.v, W.Lm, W.Dd, W.w);
+            }
+            ctl.state = TG_ST_QP;
+        }
+    }
+    if (ctl.state == TG_ST_QP) {
+        do {
+            if (ctl.need_reset) {
+                // ---- reset the BFGS factor to the identity
+                ctl.ireset++;
+                if (ctl.ireset > 5) {
+                    // relaxed convergence test after a positive directional derivative
+                    double sn = 0;
+                    #pragma unroll 1
+                    for (int i = lane; i < n; i += TG_NL) sn += W.s[i] * W.s[i];
+                    sn = sqrt(tg_wsum(sn));
+                    h3 = tg_violation(W, meq, 0);
+                    ctl.status = ((fabs(ctl.f - ctl.f0) < tol || sn < tol) && h3 < tol && !ctl.badlin && ctl.f == ctl.f) ? 0 : 8;
+                    ctl.state = TG_ST_DONE;
+                    break;
+                }
+                #pragma unroll 1
+                for (int q = lane; q < n * n; q += TG_NL) W.Lm[q] = 0;
+                #pragma unroll 1
+                for (int i = lane; i < n1; i += TG_NL) W.Dd[i] = 1;
+                TG_SYNC();
+                ctl.need_reset = 0;
+            }
+            // ---- major iteration
+            ctl.iter++;
+            if (ctl.iter > ctl.maxiter) { ctl.status = 9; ctl.state = TG_ST_DONE; break; }
+            #pragma unroll 1
+            for (int i = lane; i < n; i += TG_NL) { W.u[i] = W.xl[i] - W.x[i]; W.v[i] = W.xu[i] - W.x[i]; }
+            TG_SYNC();
+            ctl.h4 = 1;
+            int mode = tg_qp_solve(W, n, meq, 0.0);
+            ctl.badlin = 0;
+            if (mode == 6 && n == meq) mode = 4;
+            if (mode == 4) {
+                // ---- augmented problem for an inconsistent linearisation
+                ctl.badlin = 1;
+                #pragma unroll 1
+                for (int j = lane; j < m; j += TG_NL) W.A[n * W.lda + j] = j < meq ? -W.c[j] : fmax(-W.c[j], 0.0);
+                if (lane == 0) { W.g[n] = 0; W.u[n] = 0; W.v[n] = 1; }
+                TG_SYNC();
+                double rho = 100;
+                #pragma unroll 1
+                for (int incons = 0;; incons++) {
+                    mode = tg_qp_solve(W, n1, meq, rho);
+                    if (mode != 4) break;
+                    rho *= 10;
+                    if (incons + 1 > 5) break;
+                }
+                if (mode != TG_QP_OK) { ctl.status = mode; ctl.state = TG_ST_DONE; break; }
+                ctl.h4 = 1 - W.xq[n];
+            } else if (mode != TG_QP_OK) { ctl.status = mode; ctl.state = TG_ST_DONE; break; }
+            // ---- gradient of the Lagrangian at the old point, merit weights
+            #pragma unroll 1
+            for (int i = lane; i < n; i += TG_NL) {
+                double h = W.g[i];
+                #pragma unroll 1
+                for (int j = 0; j < m; j++) h -= W.A[i * W.lda + j] * W.r[j];
+                W.gl[i] = h;
+                W.s[i] = W.xq[i];
+                W.x0[i] = W.x[i];
+            }
+            ctl.f0 = ctl.f;
+            TG_SYNC();
+            double gs = 0;
+            #pragma unroll 1
+            for (int i = lane; i < n; i += TG_NL) gs += W.g[i] * W.s[i];
+            gs = tg_wsum(gs);
+            h1 = 0; h2 = 0;
+            #pragma unroll 1
+            for (int j = lane; j < m; j += TG_NL) {
+                const double cj = W.c[j];
+                h2 += fmax(-cj, j < meq ? cj : 0.0);
+                const double ar = fabs(W.r[j]);
+                W.mu[j] = fmax(ar, (W.mu[j] + ar) / 2);
+                h1 += ar * fabs(cj);
+            }
+            h1 = fabs(gs) + tg_wsum(h1);
+            h2 = tg_wsum(h2);
+            TG_SYNC();
+            if (h1 < acc && h2 < acc && !ctl.badlin && ctl.f == ctl.f) { ctl.status = 0; ctl.state = TG_ST_DONE; break; }
+            h1 = tg_violation(W, meq, W.mu);
+            ctl.t0 = ctl.f + h1;
+            h3 = gs - h1 * ctl.h4;
+            if (h3 >= 0) { ctl.need_reset = 1; break; }       // stays in state QP: the reset costs a major iteration
+            // ---- first trial point of the line search (alpha = 1)
+            ctl.alpha = 1; ctl.line = 1; ctl.h3 = h3;
+            #pragma unroll 1
+            for (int i = lane; i < n; i += TG_NL) {
+                double xv = W.x0[i] + W.s[i];
+                xv = xv < W.xl[i] ? W.xl[i] : xv;
+                xv = xv > W.xu[i] ? W.xu[i] : xv;
+                W.x[i] = xv;
+            }
+            ctl.state = TG_ST_LS;
+        } while (0);
+    }
+    TG_SYNC();
+    if (lane == 0) *W.ctl = ctl;
+    TG_SYNC();
+}
+
+// fused driver: one warp runs both stages until its problem is done (host tests; small batches)
+template <int D>
+TG_FN void tg_sqp_solve(const TgLayout &L, const int *sp, const double *par, double *xio, double *wsbase, int maxiter,
+                        double acc, int flags, TgSqpResult *res, double *trace, int trace_cap)
+{
+    TgSqpWs W;
+    tg_sqp_carve(L, wsbase, &W);
+    tg_sqp_begin(L, W, xio, maxiter, acc, flags);
+    #pragma unroll 1
+    for (;;) {
+        const int st = W.ctl->state;
+        if (st == TG_ST_DONE) break;
+        if (st == TG_ST_INIT || st == TG_ST_LS) tg_sqp_stage_ls<D>(L, sp, par, W, trace, trace_cap);
+        else tg_sqp_stage_qp(L, W);
+    }
+    #pragma unroll 1
+    for (int i = TG_LANE(); i < L.n; i += TG_NL) xio[i] = W.x[i];
+    TG_SYNC();
+    if (res && TG_LANE() == 0) {
+        res->status = W.ctl->status; res->nit = W.ctl->iter > maxiter ? maxiter : W.ctl->iter;
+        res->nfev = W.ctl->nfev; res->f = W.ctl->f;
+    }
 }
 
 #endif  // TG_SQP_H
