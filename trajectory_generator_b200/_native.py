@@ -24,23 +24,45 @@ LAYOUT_FIELDS = ("d N nint n ia is0 is1 it0 nws niw meq mineq m r_start n_start 
                  "p_tanmax p_turn p_sfc p_obs_c p_obs_r P").split()
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-shared"]
+              "-Xcompiler", "-fPIC"]
+# translation units: the host API (+ legacy single-problem kernels) and one unit per (kernel family, lanes per problem)
+UNITS = ["tg_api.cu"] + ["tg_%s_g%d.cu" % (fam, gs) for fam in ("eval", "solve") for gs in (8, 16, 32)]
+HEADERS = ["tg_sqp.h", "tg_eval.h", "tg_spec.h", "tg_shape.h", "tg_kernels_eval.inc", "tg_kernels_solve.inc"]
 
 
 def build_native(force=False, verbose=False):
-    """Compile csrc/tg_api.cu for sm_100a into lib/libTrajectoryConstraints.so (nvcc cross-compiles without a GPU)."""
-    srcs = [os.path.join(CSRC, f) for f in ("tg_api.cu", "tg_sqp.h", "tg_eval.h", "tg_spec.h")]
-    srcs.append(os.path.join(os.path.dirname(HERE), "include", "trajectory_generator_b200.h"))
-    if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(s) for s in srcs):
-        return LIB_PATH
-    os.makedirs(os.path.dirname(LIB_PATH), exist_ok=True)
+    """Compile csrc/*.cu for sm_100a into lib/libTrajectoryConstraints.so (nvcc cross-compiles without a GPU).
+    Units are compiled in parallel into lib/obj/ and linked into one shared library."""
+    from concurrent.futures import ThreadPoolExecutor
+    deps = [os.path.join(CSRC, f) for f in HEADERS]
+    deps.append(os.path.join(os.path.dirname(HERE), "include", "trajectory_generator_b200.h"))
+    objdir = os.path.join(HERE, "lib", "obj")
+    os.makedirs(objdir, exist_ok=True)
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH, srcs[0]]
-    proc = subprocess.run(cmd, capture_output=True, text=True)
-    if proc.returncode != 0:
-        raise RuntimeError("nvcc failed:\n%s\n%s" % (" ".join(cmd), proc.stderr))
+    newest_dep = max(os.path.getmtime(d) for d in deps)
+
+    def compile_unit(unit):
+        src = os.path.join(CSRC, unit)
+        obj = os.path.join(objdir, unit.replace(".cu", ".o"))
+        if not force and os.path.exists(obj) and os.path.getmtime(obj) >= max(newest_dep, os.path.getmtime(src)):
+            return obj, False, ""
+        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, src]
+        proc = subprocess.run(cmd, capture_output=True, text=True)
+        if proc.returncode != 0:
+            raise RuntimeError("nvcc failed:\n%s\n%s" % (" ".join(cmd), proc.stderr))
+        return obj, True, proc.stderr
+
+    with ThreadPoolExecutor(max_workers=min(len(UNITS), os.cpu_count() or 1)) as pool:
+        results = list(pool.map(compile_unit, UNITS))
     if verbose:
-        print(proc.stderr)
+        for _, _, log in results:
+            print(log)
+    objs = [r[0] for r in results]
+    if force or any(r[1] for r in results) or not os.path.exists(LIB_PATH):
+        cmd = [nvcc, "-shared", "-o", LIB_PATH] + objs
+        proc = subprocess.run(cmd, capture_output=True, text=True)
+        if proc.returncode != 0:
+            raise RuntimeError("link failed:\n%s\n%s" % (" ".join(cmd), proc.stderr))
     return LIB_PATH
 
 

@@ -1,28 +1,22 @@
-// CUDA kernels (sm_100a) and the C-ABI declared in include/trajectory_generator_b200.h.
+// Host side of the C-ABI declared in include/trajectory_generator_b200.h, plus the single-problem kernels
+// behind the reference's 24 legacy symbols.
 //
-// Kernels: one warp per trajectory problem.
-//   tg_eval_kernel   M1: objective, gradient, constraint rows, analytic nonlinear Jacobian rows
-//   tg_linear_kernel constant Jacobian of the linear rows
-//   tg_solve_kernel  M2: the whole SLSQP iteration of one problem per warp (tg_sqp.h),
-//                    persistent CTAs pulling problem indices from an atomic queue
-//   tg_legacy_*      single-problem kernels behind the reference's 24 C symbols
-// Data layout in HBM: row-major [B][n] variables, [B][P] parameters, [B][m] rows,
-// [B][m_nl][n] Jacobians -- a warp reads/writes its problem's rows as contiguous,
-// coalesced 8-byte accesses; per-problem working sets are staged in shared memory.
+// Device code lives in per-group-size translation units (a problem is worked on by 8, 16 or 32 lanes):
+//   tg_eval_g*.cu   M1: objective, gradient, constraint rows, analytic nonlinear Jacobian rows
+//   tg_solve_g*.cu  M2: the SLSQP iteration (tg_sqp.h) as lock-step stage kernels (+ the fused kernel, g32)
+// Data layout in HBM: row-major [B][n] variables, [B][P] parameters, [B][m] rows, [B][m_nl][n] Jacobians --
+// a lane group reads/writes its problem's rows as contiguous 8-byte accesses; per-problem working sets are
+// staged in shared memory.
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <mutex>
 #include <atomic>
 
 #include "tg_sqp.h"
+#include "tg_shape.h"
 #include "../../include/trajectory_generator_b200.h"
-
-// ---------------------------------------------------------------------------
-struct TgShape {
-    int sp[TG_SP_COUNT];
-    TgLayout L;
-};
 
 static thread_local char g_err[512] = "";
 static std::atomic<unsigned long long> g_launches{0};
@@ -52,132 +46,10 @@ static int tg_make_shape(const int *spec, TgShape *S)
     return 0;
 }
 
-// ---------------------------------------------------------------------------
-// M1 evaluation kernel
-// ---------------------------------------------------------------------------
-constexpr int EVAL_WARPS = 4;
-constexpr int SOLVE_MIN_CTAS = 4;      // 4 CTAs x 4 warps per SM -> at most 128 registers per thread
-
-__device__ __forceinline__ int tg_eval_smem_doubles(const TgLayout &L)
-{
-    return L.n + L.P + L.m + tg_scratch_doubles(L) + 4;
-}
-
-template <int D>
-__global__ void __launch_bounds__(EVAL_WARPS * 32)
-tg_eval_kernel(const TgShape S, int B, const double *__restrict__ par, const double *__restrict__ x,
-               double *__restrict__ f, double *__restrict__ g, double *__restrict__ c, double *__restrict__ jnl)
-{
-    extern __shared__ double smem[];
-    const TgLayout &L = S.L;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int per = tg_eval_smem_doubles(L);
-    double *sx = smem + warp * per, *sp_ = sx + L.n, *sc = sp_ + L.P, *scr = sc + L.m;
-    const int stride = gridDim.x * EVAL_WARPS;
-    for (int b = blockIdx.x * EVAL_WARPS + warp; b < B; b += stride) {
-        for (int i = lane; i < L.n; i += 32) sx[i] = x[(size_t)b * L.n + i];
-        for (int i = lane; i < L.P; i += 32) sp_[i] = par[(size_t)b * L.P + i];
-        __syncwarp();
-        const double fv = tg_objective(L, S.sp, sx, g ? g + (size_t)b * L.n : nullptr);
-        if (f && lane == 0) f[b] = fv;
-        if (c || jnl) {
-            TgJac sink = {jnl ? jnl + (size_t)b * L.m_nl * L.n : nullptr, L.n, 1, 1};
-            tg_constraints_d<D>(L, S.sp, sp_, sx, sc, jnl ? &sink : nullptr, scr);
-            if (c)
-                for (int j = lane; j < L.m; j += 32) c[(size_t)b * L.m + j] = sc[j];
-        }
-        __syncwarp();
-    }
-}
-
-template <int D>
-__global__ void __launch_bounds__(EVAL_WARPS * 32)
-tg_linear_kernel(const TgShape S, int B, const double *__restrict__ par, double *__restrict__ alin)
-{
-    extern __shared__ double smem[];
-    const TgLayout &L = S.L;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double *sp_ = smem + warp * (L.P + 1);
-    const int stride = gridDim.x * EVAL_WARPS;
-    for (int b = blockIdx.x * EVAL_WARPS + warp; b < B; b += stride) {
-        for (int i = lane; i < L.P; i += 32) sp_[i] = par[(size_t)b * L.P + i];
-        __syncwarp();
-        TgJac sink = {alin + (size_t)b * L.m * L.n, L.n, 1, 0};
-        tg_linear_jacobian_d<D>(L, S.sp, sp_, sink);
-        __syncwarp();
-    }
-}
-
-// ---------------------------------------------------------------------------
-// M2 solve kernel
-// ---------------------------------------------------------------------------
-// the reference's is_violation: violation flags of the LAST constraint in its list, tolerance 10e-6
-// (TG/trajectory_generator.py:252-261, DS/constraint_function_data.py:12,45-48)
-__device__ int tg_last_block_violation(const TgLayout &L, const double *c)
-{
-    int r0, r1, eq = 0;
-    if (L.n_obs) { r0 = L.r_obs; r1 = r0 + L.n_obs; }
-    else if (L.n_sfc) { r0 = L.r_sfcl; r1 = r0 + 2 * L.n_sfc; }
-    else if (L.n_turn) { r0 = L.r_turn; r1 = r0 + 1; }
-    else if (L.n_tan) { r0 = L.r_tanl; r1 = r0 + 2 * L.n_tan; }
-    else if (L.n_db) { r0 = L.r_db; r1 = r0 + L.n_db; }
-    else if (L.n_iwv) { r0 = L.r_iwv; r1 = r0 + L.n_iwv; eq = 1; }
-    else if (L.n_iwl) { r0 = L.r_iwl; r1 = r0 + L.n_iwl; eq = 1; }
-    else if (L.n_eder) { r0 = L.r_eder; r1 = r0 + L.n_eder; eq = 1; }
-    else if (L.n_sder) { r0 = L.r_sder; r1 = r0 + L.n_sder; eq = 1; }
-    else { r0 = L.r_end; r1 = r0 + L.n_end; eq = 1; }
-    int bad = 0;
-    for (int j = r0 + (threadIdx.x & 31); j < r1; j += 32) {
-        const double v = c[j];
-        if (eq ? (fabs(v) > 10e-6) : (v < -10e-6)) bad = 1;
-        if (v != v) bad = 1;
-    }
-    return __any_sync(0xffffffffu, bad);
-}
-
-template <int D>
-__global__ void __launch_bounds__(128, SOLVE_MIN_CTAS)
-tg_solve_kernel(const TgShape S, int B, const double *__restrict__ par, double *__restrict__ x,
-                                double *__restrict__ fout, int *__restrict__ status, int *__restrict__ nit,
-                                int *__restrict__ violation, int maxiter, double ftol, int flags,
-                                double *gws, size_t ws_doubles, int warps_per_cta, int *queue)
-{
-    extern __shared__ double smem[];
-    const TgLayout &L = S.L;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    // per-warp slice: parameters + (shared-memory workspace | pointer into the global one)
-    double *spar = smem + (size_t)warp * (L.P + (gws ? 0 : ws_doubles) + 2);
-    double *ws = gws ? gws + ((size_t)blockIdx.x * warps_per_cta + warp) * ws_doubles : spar + L.P + 1;
-    for (;;) {
-        int b = 0;
-        if (lane == 0) b = atomicAdd(queue, 1);
-        b = __shfl_sync(0xffffffffu, b, 0);
-        if (b >= B) break;
-        for (int i = lane; i < L.P; i += 32) spar[i] = par[(size_t)b * L.P + i];
-        __syncwarp();
-        TgSqpResult res;
-        tg_sqp_solve<D>(L, S.sp, spar, x + (size_t)b * L.n, ws, maxiter, ftol, flags, &res, nullptr, 0);
-        res.status = __shfl_sync(0xffffffffu, res.status, 0);
-        int viol = 0;
-        if (res.status != 0) {
-            TgSqpWs W;
-            tg_sqp_carve(L, ws, &W);
-            viol = tg_last_block_violation(L, W.c);
-        }
-        if (lane == 0) {
-            if (status) status[b] = res.status;
-            if (nit) nit[b] = res.nit;
-            if (fout) fout[b] = res.f;
-            if (violation) violation[b] = viol;
-        }
-        __syncwarp();
-    }
-}
-
-// ---------------------------------------------------------------------------
-// launch helpers
-// ---------------------------------------------------------------------------
 static int g_sm_count = 0, g_smem_optin = 0;
+template <int D>
+__global__ void tg_legacy_kernel(int what, const double *pts, int N, double alpha, int kind, const double *centers,
+                                 const double *radii, int K, double *out);
 
 extern "C" int tg_device_check(void)
 {
@@ -187,7 +59,7 @@ extern "C" int tg_device_check(void)
     int dev = 0;
     TG_CUDA(cudaGetDevice(&dev));
     cudaFuncAttributes attr;
-    e = cudaFuncGetAttributes(&attr, tg_eval_kernel<2>);
+    e = cudaFuncGetAttributes(&attr, tg_legacy_kernel<2>);
     if (e != cudaSuccess) return tg_fail(11, "no kernel image for this device (built for sm_100a)", e);
     TG_CUDA(cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev));
     TG_CUDA(cudaDeviceGetAttribute(&g_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
@@ -210,6 +82,25 @@ extern "C" int tg_layout(const int *spec, int *out, int cap)
 extern "C" const char *tg_last_error(void) { return g_err; }
 extern "C" unsigned long long tg_launch_count(void) { return g_launches.load(); }
 
+// ---------------------------------------------------------------------------
+// lanes per problem.  Heuristic: enough lanes for the per-interval terms (the longest per-lane chains), capped by
+// what shared memory allows; TG_EVAL_GS / TG_LS_GS / TG_QP_GS (8, 16, 32) override for tuning.
+// ---------------------------------------------------------------------------
+static int tg_env_gs(const char *name, int dflt)
+{
+    const char *v = getenv(name);
+    if (!v) return dflt;
+    const int g = atoi(v);
+    return (g == 8 || g == 16 || g == 32) ? g : dflt;
+}
+
+static int tg_default_gs(const TgLayout &L)
+{
+    return L.nint <= 8 ? 8 : (L.nint <= 16 ? 16 : 32);
+}
+
+#define TG_DISPATCH(gs, call8, call16, call32) ((gs) == 8 ? (call8) : (gs) == 16 ? (call16) : (call32))
+
 extern "C" int tg_eval_batch(const int *spec, int B, const double *par, const double *x, double *f, double *g,
                              double *c, double *jnl, void *stream)
 {
@@ -218,17 +109,13 @@ extern "C" int tg_eval_batch(const int *spec, int B, const double *par, const do
     if (rc) return rc;
     if (B <= 0) return 0;
     if ((rc = tg_device_check())) return rc;
-    const size_t smem = (size_t)EVAL_WARPS * (S.L.n + S.L.P + S.L.m + tg_scratch_doubles(S.L) + 4) * sizeof(double);
-    if (smem > (size_t)g_smem_optin) return tg_fail(3, "problem shape too large for the evaluation kernel's shared memory");
-    if (S.L.d == 2) TG_CUDA(cudaFuncSetAttribute(tg_eval_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    else TG_CUDA(cudaFuncSetAttribute(tg_eval_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int grid = (B + EVAL_WARPS - 1) / EVAL_WARPS;
-    const int cap = g_sm_count * 16;
-    if (grid > cap) grid = cap;
-    if (S.L.d == 2) tg_eval_kernel<2><<<grid, EVAL_WARPS * 32, smem, (cudaStream_t)stream>>>(S, B, par, x, f, g, c, jnl);
-    else tg_eval_kernel<3><<<grid, EVAL_WARPS * 32, smem, (cudaStream_t)stream>>>(S, B, par, x, f, g, c, jnl);
+    const int gs = tg_env_gs("TG_EVAL_GS", tg_default_gs(S.L));
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = TG_DISPATCH(gs, tg_launch_eval_g8(S, B, par, x, f, g, c, jnl, g_sm_count, g_smem_optin, st),
+                                tg_launch_eval_g16(S, B, par, x, f, g, c, jnl, g_sm_count, g_smem_optin, st),
+                                tg_launch_eval_g32(S, B, par, x, f, g, c, jnl, g_sm_count, g_smem_optin, st));
     g_launches++;
-    TG_CUDA(cudaGetLastError());
+    if (e != cudaSuccess) return tg_fail(100 + (int)e, "tg_eval_kernel launch", e);
     return 0;
 }
 
@@ -239,117 +126,36 @@ extern "C" int tg_linear_rows_batch(const int *spec, int B, const double *par, d
     if (rc) return rc;
     if (B <= 0) return 0;
     if ((rc = tg_device_check())) return rc;
-    const size_t smem = (size_t)EVAL_WARPS * (S.L.P + 1) * sizeof(double);
-    int grid = (B + EVAL_WARPS - 1) / EVAL_WARPS;
-    const int cap = g_sm_count * 16;
-    if (grid > cap) grid = cap;
-    if (S.L.d == 2) tg_linear_kernel<2><<<grid, EVAL_WARPS * 32, smem, (cudaStream_t)stream>>>(S, B, par, alin);
-    else tg_linear_kernel<3><<<grid, EVAL_WARPS * 32, smem, (cudaStream_t)stream>>>(S, B, par, alin);
+    cudaError_t e = tg_launch_linear_g32(S, B, par, alin, g_sm_count, (cudaStream_t)stream);
     g_launches++;
-    TG_CUDA(cudaGetLastError());
+    if (e != cudaSuccess) return tg_fail(100 + (int)e, "tg_linear_kernel launch", e);
     return 0;
 }
 
 // ---------------------------------------------------------------------------
-// M2, lock-step form: the two stages of tg_sqp.h as separate kernels over the whole batch.  Every warp of
-// the machine then runs the same few functions at the same time (the fused kernel is bound by
-// instruction-cache misses: each warp sits in a different phase of a ~300 KB program).  Per-problem state
-// lives in a global workspace and is staged through shared memory inside a stage when it fits.
+// M2 launch plans
 // ---------------------------------------------------------------------------
-constexpr int STAGE_WARPS = 4;
-
-template <int D>
-__global__ void __launch_bounds__(STAGE_WARPS * 32)
-tg_sqp_begin_kernel(const TgShape S, int B, const double *__restrict__ x, double *pws, size_t np, int maxiter, double ftol,
-                    int flags)
-{
-    const int warp = threadIdx.x >> 5;
-    const int b = blockIdx.x * STAGE_WARPS + warp;
-    if (b >= B) return;
-    TgSqpWs W;
-    size_t a, c;
-    tg_sqp_carve2(S.L, pws + (size_t)b * np, nullptr, &W, &a, &c);
-    tg_sqp_begin(S.L, W, x + (size_t)b * S.L.n, maxiter, ftol, flags);
-}
-
-// STAGE 0: line search / first evaluation.  STAGE 1: update + QP.
-template <int D, int STAGE>
-__global__ void __launch_bounds__(STAGE_WARPS * 32, 4)
-tg_sqp_stage_kernel(const TgShape S, int B, const double *__restrict__ par, double *pws, size_t np, size_t ns, int staged,
-                    int *counters)
-{
-    extern __shared__ double smem[];
-    const TgLayout &L = S.L;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int b = blockIdx.x * STAGE_WARPS + warp;
-    if (b >= B) return;
-    double *gp = pws + (size_t)b * np;
-    const int st = ((const TgSqpCtl *)gp)->state;
-    if (STAGE == 0 ? !(st == TG_ST_INIT || st == TG_ST_LS) : !(st == TG_ST_UPDATE || st == TG_ST_QP)) return;
-    const size_t per = (size_t)L.P + 1 + ns + (staged ? np : 0);
-    double *spar = smem + (size_t)warp * per, *sscr = spar + L.P + 1, *spers = sscr + ns;
-    if (STAGE == 0)
-        for (int i = lane; i < L.P; i += 32) spar[i] = par[(size_t)b * L.P + i];
-    if (staged)
-        for (size_t i = lane; i < np; i += 32) spers[i] = gp[i];
-    __syncwarp();
-    TgSqpWs W;
-    size_t a, c;
-    tg_sqp_carve2(L, staged ? spers : gp, sscr, &W, &a, &c);
-    if (STAGE == 0) tg_sqp_stage_ls<D>(L, S.sp, spar, W, nullptr, 0);
-    else tg_sqp_stage_qp(L, W);
-    __syncwarp();
-    if (STAGE == 1 && lane == 0 && W.ctl->state == TG_ST_DONE) atomicAdd(counters, 1);
-    if (staged)
-        for (size_t i = lane; i < np; i += 32) gp[i] = spers[i];
-}
-
-__global__ void tg_sqp_finish_kernel(const TgShape S, int B, const double *pws, size_t np, double *__restrict__ x,
-                                     double *__restrict__ fout, int *__restrict__ status, int *__restrict__ nit,
-                                     int *__restrict__ violation)
-{
-    const TgLayout &L = S.L;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int b = blockIdx.x * STAGE_WARPS + warp;
-    if (b >= B) return;
-    TgSqpWs W;
-    size_t a, c;
-    tg_sqp_carve2(L, const_cast<double *>(pws) + (size_t)b * np, nullptr, &W, &a, &c);
-    for (int i = lane; i < L.n; i += 32) x[(size_t)b * L.n + i] = W.x[i];
-    const TgSqpCtl ctl = *W.ctl;
-    int viol = 0;
-    if (ctl.status != 0) viol = tg_last_block_violation(L, W.c);
-    if (lane == 0) {
-        if (status) status[b] = ctl.status;
-        if (nit) nit[b] = ctl.iter > ctl.maxiter ? ctl.maxiter : ctl.iter;
-        if (fout) fout[b] = ctl.f;
-        if (violation) violation[b] = viol;
-    }
-}
-
-// launch geometry for a shape
 struct TgSolvePlan {
     // fused kernel
     int warps_per_cta, ctas, use_global;
     size_t ws_doubles, smem_bytes, global_bytes;
     // lock-step kernels
-    size_t np, ns, stage_smem;
-    int staged, chunk;
+    size_t np, smem_ls, smem_qp;
+    int staged, chunk, gs_ls, gs_qp;
     size_t phased_bytes;
 };
 
-#define TG_PHASED_CHUNK_BYTES ((size_t)6 << 30)     // per-chunk cap of the global state (problems are solved in chunks)
+#define TG_PHASED_CHUNK_BYTES ((size_t)6 << 30)     // cap of the global state per chunk (the batch is solved in chunks)
 
 static int tg_plan_solve(const TgShape &S, int B, TgSolvePlan *P)
 {
     int rc = tg_device_check();
     if (rc) return rc;
+    const size_t budget = (size_t)g_smem_optin - 1024;
+    const size_t sm_total = 227 * 1024;
+    // ---- fused: shared-memory workspace when at least 8 warps fit on an SM, else global workspace
     P->ws_doubles = tg_sqp_workspace_doubles(S.L);
     const size_t per_warp_shared = (S.L.P + P->ws_doubles + 2) * sizeof(double);
-    const size_t budget = (size_t)g_smem_optin - 1024;
-    // shared-memory workspace when at least 8 warps fit on an SM; otherwise the workspace lives in
-    // global memory (L1/L2 resident) and only the parameter row is staged
-    const size_t sm_total = 227 * 1024;
     if (per_warp_shared * 8 <= sm_total) {
         P->use_global = 0;
         P->warps_per_cta = 4;
@@ -364,7 +170,7 @@ static int tg_plan_solve(const TgShape &S, int B, TgSolvePlan *P)
         P->use_global = 1;
         P->warps_per_cta = 4;
         P->smem_bytes = (size_t)P->warps_per_cta * (S.L.P + 2) * sizeof(double);
-        P->ctas = g_sm_count * 4;     // 16 warps per SM
+        P->ctas = g_sm_count * 4;
         P->global_bytes = (size_t)P->ctas * P->warps_per_cta * P->ws_doubles * sizeof(double);
     }
     const int need = (B + P->warps_per_cta - 1) / P->warps_per_cta;
@@ -372,14 +178,25 @@ static int tg_plan_solve(const TgShape &S, int B, TgSolvePlan *P)
         P->ctas = need > 0 ? need : 1;
         if (P->use_global) P->global_bytes = (size_t)P->ctas * P->warps_per_cta * P->ws_doubles * sizeof(double);
     }
-    // lock-step plan: stage the persistent state through shared memory when 16 warps still fit on an SM
+    // ---- lock step
     P->np = tg_sqp_persistent_doubles(S.L);
-    P->ns = tg_sqp_scratch_doubles(S.L);
-    const size_t with_state = ((size_t)S.L.P + 1 + P->ns + P->np) * sizeof(double) * STAGE_WARPS;
-    const size_t without = ((size_t)S.L.P + 1 + P->ns) * sizeof(double) * STAGE_WARPS;
+    // line search: smallest group that leaves >= 8 resident warps' worth of shared memory per SM
+    int gs = tg_env_gs("TG_LS_GS", tg_default_gs(S.L));
+    for (;;) {
+        P->smem_ls = TG_DISPATCH(gs, tg_ls_smem_g8(S), tg_ls_smem_g16(S), tg_ls_smem_g32(S));
+        if (P->smem_ls * 2 <= sm_total - 2048 || gs == 32) break;
+        gs *= 2;
+    }
+    if (P->smem_ls > budget) return tg_fail(3, "problem shape too large for the line-search kernel's shared memory");
+    P->gs_ls = gs;
+    // QP: full warp per problem by default; persistent state staged through shared memory when 16 warps still fit
+    gs = tg_env_gs("TG_QP_GS", 32);
+    P->gs_qp = gs;
+    const size_t with_state = TG_DISPATCH(gs, tg_qp_smem_g8(S, 1), tg_qp_smem_g16(S, 1), tg_qp_smem_g32(S, 1));
+    const size_t without = TG_DISPATCH(gs, tg_qp_smem_g8(S, 0), tg_qp_smem_g16(S, 0), tg_qp_smem_g32(S, 0));
     P->staged = with_state * 4 <= sm_total - 4096;
-    P->stage_smem = P->staged ? with_state : without;
-    if (P->stage_smem > budget) return tg_fail(3, "problem shape too large for the solve kernels' shared memory");
+    P->smem_qp = P->staged ? with_state : without;
+    if (P->smem_qp > budget) return tg_fail(3, "problem shape too large for the QP kernel's shared memory");
     size_t chunk = TG_PHASED_CHUNK_BYTES / (P->np * sizeof(double));
     if (chunk < 1024) chunk = 1024;
     if (chunk > (size_t)B) chunk = (size_t)B;
@@ -397,52 +214,41 @@ extern "C" size_t tg_solve_workspace_bytes(const int *spec, int B)
     return need + 256;     // + counters
 }
 
-template <int D>
-static int tg_solve_fused(const TgShape &S, const TgSolvePlan &P, int B, const double *par, double *x, double *f,
-                          int *status, int *nit, int *violation, int maxiter, double ftol, int flags, int *queue,
-                          double *gws, cudaStream_t st)
-{
-    TG_CUDA(cudaFuncSetAttribute(tg_solve_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.smem_bytes));
-    tg_solve_kernel<D><<<P.ctas, P.warps_per_cta * 32, P.smem_bytes, st>>>(S, B, par, x, f, status, nit, violation, maxiter,
-                                                                           ftol, flags, P.use_global ? gws : nullptr,
-                                                                           P.ws_doubles, P.warps_per_cta, queue);
-    g_launches++;
-    TG_CUDA(cudaGetLastError());
-    return 0;
-}
+#define TG_LAUNCH(call, what)                                                   \
+    do {                                                                        \
+        cudaError_t e_ = (call);                                                \
+        g_launches++;                                                           \
+        if (e_ != cudaSuccess) return tg_fail(100 + (int)e_, what, e_);         \
+    } while (0)
 
-template <int D>
 static int tg_solve_phased(const TgShape &S, const TgSolvePlan &P, int B, const double *par, double *x, double *f,
                            int *status, int *nit, int *violation, int maxiter, double ftol, int flags, int *counters,
                            double *pws, cudaStream_t st)
 {
-    TG_CUDA(cudaFuncSetAttribute(tg_sqp_stage_kernel<D, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.stage_smem));
-    TG_CUDA(cudaFuncSetAttribute(tg_sqp_stage_kernel<D, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.stage_smem));
     const TgLayout &L = S.L;
     for (int lo = 0; lo < B; lo += P.chunk) {
         const int nb = B - lo < P.chunk ? B - lo : P.chunk;
-        const int grid = (nb + STAGE_WARPS - 1) / STAGE_WARPS;
         const double *cpar = par + (size_t)lo * L.P;
         double *cx = x + (size_t)lo * L.n;
         TG_CUDA(cudaMemsetAsync(counters, 0, 256, st));
-        tg_sqp_begin_kernel<D><<<grid, STAGE_WARPS * 32, 0, st>>>(S, nb, cx, pws, P.np, maxiter, ftol, flags);
-        g_launches++;
+        TG_LAUNCH(tg_launch_begin_g32(S, nb, cx, pws, P.np, maxiter, ftol, flags, st), "tg_sqp_begin_kernel");
         int done = 0;
         // each round = one SLSQP major iteration of every unfinished problem; maxiter + 1 rounds finish everything
         for (int round = 0; round <= maxiter + 1 && done < nb; round++) {
-            tg_sqp_stage_kernel<D, 0><<<grid, STAGE_WARPS * 32, P.stage_smem, st>>>(S, nb, cpar, pws, P.np, P.ns, P.staged, counters);
-            tg_sqp_stage_kernel<D, 1><<<grid, STAGE_WARPS * 32, P.stage_smem, st>>>(S, nb, cpar, pws, P.np, P.ns, P.staged, counters);
-            g_launches += 2;
+            TG_LAUNCH(TG_DISPATCH(P.gs_ls, tg_launch_ls_g8(S, nb, cpar, pws, P.np, P.smem_ls, st),
+                                  tg_launch_ls_g16(S, nb, cpar, pws, P.np, P.smem_ls, st),
+                                  tg_launch_ls_g32(S, nb, cpar, pws, P.np, P.smem_ls, st)), "tg_sqp_ls_kernel");
+            TG_LAUNCH(TG_DISPATCH(P.gs_qp, tg_launch_qp_g8(S, nb, pws, P.np, P.staged, P.smem_qp, counters, st),
+                                  tg_launch_qp_g16(S, nb, pws, P.np, P.staged, P.smem_qp, counters, st),
+                                  tg_launch_qp_g32(S, nb, pws, P.np, P.staged, P.smem_qp, counters, st)), "tg_sqp_qp_kernel");
             if ((round & 7) == 7) {      // poll the number of finished problems
                 TG_CUDA(cudaMemcpyAsync(&done, counters, sizeof(int), cudaMemcpyDeviceToHost, st));
                 TG_CUDA(cudaStreamSynchronize(st));
             }
         }
-        tg_sqp_finish_kernel<<<grid, STAGE_WARPS * 32, 0, st>>>(S, nb, pws, P.np, cx, f ? f + lo : nullptr,
-                                                               status ? status + lo : nullptr, nit ? nit + lo : nullptr,
-                                                               violation ? violation + lo : nullptr);
-        g_launches++;
-        TG_CUDA(cudaGetLastError());
+        TG_LAUNCH(tg_launch_finish_g32(S, nb, pws, P.np, cx, f ? f + lo : nullptr, status ? status + lo : nullptr,
+                                       nit ? nit + lo : nullptr, violation ? violation + lo : nullptr, st),
+                  "tg_sqp_finish_kernel");
     }
     return 0;
 }
@@ -465,11 +271,12 @@ extern "C" int tg_solve_batch(const int *spec, int B, const double *par, double 
     cudaStream_t st = (cudaStream_t)stream;
     if (flags & TG_SOLVE_FUSED) {
         TG_CUDA(cudaMemsetAsync(counters, 0, 256, st));
-        return S.L.d == 2 ? tg_solve_fused<2>(S, P, B, par, x, f, status, nit, violation, maxiter, ftol, flags, counters, gws, st)
-                          : tg_solve_fused<3>(S, P, B, par, x, f, status, nit, violation, maxiter, ftol, flags, counters, gws, st);
+        TG_LAUNCH(tg_launch_fused_g32(S, B, par, x, f, status, nit, violation, maxiter, ftol, flags,
+                                      P.use_global ? gws : nullptr, P.ws_doubles, P.warps_per_cta, P.ctas, P.smem_bytes,
+                                      counters, st), "tg_solve_kernel");
+        return 0;
     }
-    return S.L.d == 2 ? tg_solve_phased<2>(S, P, B, par, x, f, status, nit, violation, maxiter, ftol, flags, counters, gws, st)
-                      : tg_solve_phased<3>(S, P, B, par, x, f, status, nit, violation, maxiter, ftol, flags, counters, gws, st);
+    return tg_solve_phased(S, P, B, par, x, f, status, nit, violation, maxiter, ftol, flags, counters, gws, st);
 }
 
 // ---------------------------------------------------------------------------

@@ -25,18 +25,30 @@
 
 #define TG_PI 3.14159265358979323846
 
-// TG_HD (tg_spec.h) force-inlines small helpers; TG_FN is for the large block evaluators
-// (kept out of line on the device: the kernels are instruction-cache bound when everything is inlined)
+// TG_HD (tg_spec.h) force-inlines small helpers; TG_FN is for the large block evaluators.  A translation
+// unit may define TG_INLINE_ALL (kernels in which every warp runs the same code: inlining pays) -- the
+// solver stages keep them out of line (instruction-cache footprint).
 #if defined(__CUDACC__)
-#define TG_FN __host__ __device__ __noinline__
+#if defined(TG_INLINE_ALL)
+#define TG_FN static __host__ __device__ inline
+#else
+#define TG_FN static __host__ __device__ __noinline__
+#endif
 #else
 #define TG_FN static inline
 #endif
 
+// A problem is evaluated by a GROUP of TG_GS consecutive lanes of a warp (TG_GS = 8, 16 or 32, fixed per
+// translation unit): with 5..14 intervals per spline a full warp leaves most lanes idle in the per-interval
+// terms, so several problems share a warp.  Syncs and shuffles only involve the lanes of the group.
+#ifndef TG_GS
+#define TG_GS 32
+#endif
 #if defined(__CUDA_ARCH__)
-#define TG_LANE() ((int)(threadIdx.x & 31))
-#define TG_NL 32
-#define TG_SYNC() __syncwarp()
+#define TG_LANE() ((int)(threadIdx.x & (TG_GS - 1)))
+#define TG_NL TG_GS
+#define TG_GMASK() (TG_GS == 32 ? 0xffffffffu : (((1u << (TG_GS & 31)) - 1u) << ((threadIdx.x & 31u) & ~(unsigned)(TG_GS - 1))))
+#define TG_SYNC() __syncwarp(TG_GMASK())
 #else
 #define TG_LANE() 0
 #define TG_NL 1
@@ -44,13 +56,13 @@
 #endif
 
 // ---------------------------------------------------------------------------
-// warp folds (identity on the host build)
+// group folds (identity on the host build)
 // ---------------------------------------------------------------------------
 TG_HD double tg_wsum(double v)
 {
 #if defined(__CUDA_ARCH__)
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    for (int o = TG_GS / 2; o > 0; o >>= 1) v += __shfl_xor_sync(TG_GMASK(), v, o);
 #endif
     return v;
 }
@@ -60,9 +72,9 @@ TG_HD void tg_wargmax(double &v, int &i)
 {
 #if defined(__CUDA_ARCH__)
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        double ov = __shfl_xor_sync(0xffffffffu, v, o);
-        int oi = __shfl_xor_sync(0xffffffffu, i, o);
+    for (int o = TG_GS / 2; o > 0; o >>= 1) {
+        double ov = __shfl_xor_sync(TG_GMASK(), v, o);
+        int oi = __shfl_xor_sync(TG_GMASK(), i, o);
         if (ov > v || (ov == v && oi < i)) { v = ov; i = oi; }
     }
 #endif
@@ -72,9 +84,9 @@ TG_HD void tg_wargmin(double &v, int &i)
 {
 #if defined(__CUDA_ARCH__)
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        double ov = __shfl_xor_sync(0xffffffffu, v, o);
-        int oi = __shfl_xor_sync(0xffffffffu, i, o);
+    for (int o = TG_GS / 2; o > 0; o >>= 1) {
+        double ov = __shfl_xor_sync(TG_GMASK(), v, o);
+        int oi = __shfl_xor_sync(TG_GMASK(), i, o);
         if (ov < v || (ov == v && oi < i)) { v = ov; i = oi; }
     }
 #endif
@@ -83,10 +95,19 @@ TG_HD void tg_wargmin(double &v, int &i)
 TG_HD double tg_bcast(double v, int src)
 {
 #if defined(__CUDA_ARCH__)
-    return __shfl_sync(0xffffffffu, v, src);
+    return __shfl_sync(TG_GMASK(), v, src, TG_GS);
 #else
     (void)src;
     return v;
+#endif
+}
+
+TG_HD int tg_any(int pred)
+{
+#if defined(__CUDA_ARCH__)
+    return __any_sync(TG_GMASK(), pred) != 0;
+#else
+    return pred != 0;
 #endif
 }
 

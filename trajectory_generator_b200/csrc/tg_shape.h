@@ -1,0 +1,47 @@
+// Shared between the host API (tg_api.cu) and the per-group-size kernel translation units.
+#ifndef TG_SHAPE_H
+#define TG_SHAPE_H
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include "tg_spec.h"
+
+struct TgShape {
+    int sp[TG_SP_COUNT];
+    TgLayout L;
+};
+
+// launch description of the lock-step solve stages
+struct TgStageLaunch {
+    int B;                // problems in this chunk
+    size_t np;            // persistent doubles per problem
+    int staged_qp;        // QP stage: persistent state staged through shared memory
+    size_t smem_ls, smem_qp;
+    int threads;          // threads per CTA
+};
+
+#define TG_DECLARE_VARIANT(SFX)                                                                                           \
+    cudaError_t tg_launch_eval##SFX(const TgShape &S, int B, const double *par, const double *x, double *f, double *g,    \
+                                    double *c, double *jnl, int sm_count, int smem_optin, cudaStream_t st);               \
+    cudaError_t tg_launch_linear##SFX(const TgShape &S, int B, const double *par, double *alin, int sm_count,             \
+                                      cudaStream_t st);                                                                   \
+    size_t tg_eval_smem##SFX(const TgShape &S);                                                                           \
+    cudaError_t tg_launch_begin##SFX(const TgShape &S, int B, const double *x, double *pws, size_t np, int maxiter,       \
+                                     double ftol, int flags, cudaStream_t st);                                            \
+    cudaError_t tg_launch_ls##SFX(const TgShape &S, int B, const double *par, double *pws, size_t np, size_t smem,        \
+                                  cudaStream_t st);                                                                       \
+    cudaError_t tg_launch_qp##SFX(const TgShape &S, int B, double *pws, size_t np, int staged, size_t smem, int *counters, \
+                                  cudaStream_t st);                                                                       \
+    size_t tg_ls_smem##SFX(const TgShape &S);                                                                             \
+    size_t tg_qp_smem##SFX(const TgShape &S, int staged);                                                                 \
+    cudaError_t tg_launch_finish##SFX(const TgShape &S, int B, const double *pws, size_t np, double *x, double *f,        \
+                                      int *status, int *nit, int *violation, cudaStream_t st);
+
+TG_DECLARE_VARIANT(_g8)
+TG_DECLARE_VARIANT(_g16)
+TG_DECLARE_VARIANT(_g32)
+
+// fused kernel (group size 32 only)
+cudaError_t tg_launch_fused_g32(const TgShape &S, int B, const double *par, double *x, double *f, int *status, int *nit,
+                                int *violation, int maxiter, double ftol, int flags, double *gws, size_t ws_doubles,
+                                int warps_per_cta, int ctas, size_t smem, int *queue, cudaStream_t st);
+#endif

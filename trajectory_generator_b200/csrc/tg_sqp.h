@@ -54,32 +54,48 @@ struct TgSqpWs {
 
 TG_HD int tg_odd(int v) { return v | 1; }
 
-// carves the two regions; returns their sizes in doubles through np_ / ns_
-TG_HD void tg_sqp_carve2(const TgLayout &L, double *pbase, double *sbase, TgSqpWs *W, size_t *np_, size_t *ns_)
+// Carves the per-problem state.  The persistent block is [ctl | x xl xu g s x0 | c mu | gl r Lm Dd | A]; its first
+// `npre` doubles (everything the line-search stage touches except A) may be staged at `prefix` while the rest
+// stays at `pbase` (+ offset) -- pass prefix == pbase for one contiguous block.  Sizes come back in doubles.
+TG_HD void tg_sqp_carve3(const TgLayout &L, double *prefix, double *pbase, double *sbase, TgSqpWs *W, size_t *np_,
+                         size_t *ns_, size_t *npre_)
 {
     const int n = L.n, n1 = n + 1, m = L.m;
     TgSqpWs w;
     w.n = n; w.n1 = n1; w.m = m; w.lda = tg_odd(m > 0 ? m : 1); w.ldq = tg_odd(n1); w.nc = m + 2 * n1;
     size_t o = 0;
-    double *base = pbase;
+    double *base = prefix;
 #define TG_TAKE(field, count) w.field = base ? base + o : 0; o += (size_t)(count)
     w.ctl = (TgSqpCtl *)base; o += TG_CTL_DOUBLES;
-    TG_TAKE(x, n1); TG_TAKE(xl, n1); TG_TAKE(xu, n1); TG_TAKE(g, n1); TG_TAKE(s, n1); TG_TAKE(x0, n1); TG_TAKE(gl, n1);
-    TG_TAKE(c, m + 1); TG_TAKE(mu, m + 1); TG_TAKE(r, w.nc + 1);
+    TG_TAKE(x, n1); TG_TAKE(xl, n1); TG_TAKE(xu, n1); TG_TAKE(g, n1); TG_TAKE(s, n1); TG_TAKE(x0, n1);
+    TG_TAKE(c, m + 1); TG_TAKE(mu, m + 1);
+    if (npre_) *npre_ = o;
+    base = pbase;
+    TG_TAKE(gl, n1); TG_TAKE(r, w.nc + 1);
     TG_TAKE(Lm, n * n); TG_TAKE(Dd, n1);
     TG_TAKE(A, w.lda * n1);
     if (np_) *np_ = o;
     o = 0; base = sbase;
-    TG_TAKE(u, n1); TG_TAKE(v, n1); TG_TAKE(w, n1); TG_TAKE(cf, m + 1);
+    TG_TAKE(cf, m + 1); TG_TAKE(scratch, tg_scratch_doubles(L));       // <- all the line-search stage needs
+    TG_TAKE(u, n1); TG_TAKE(v, n1); TG_TAKE(w, n1);
     TG_TAKE(Jq, w.ldq * n1); TG_TAKE(R, w.ldq * n1);
     TG_TAKE(z, n1); TG_TAKE(dq, n1); TG_TAKE(rq, n1); TG_TAKE(np, n1); TG_TAKE(uq, n1 + 1); TG_TAKE(xq, n1); TG_TAKE(hw, n1);
-    TG_TAKE(scratch, tg_scratch_doubles(L));
     double *ints = base ? base + o : 0; o += (size_t)((n1 + 1 + w.nc + 1) / 2 + 1);
     w.act = (int *)ints; w.iact = w.act + n1 + 1;
 #undef TG_TAKE
     if (ns_) *ns_ = o;
     if (W) *W = w;
 }
+
+TG_HD void tg_sqp_carve2(const TgLayout &L, double *pbase, double *sbase, TgSqpWs *W, size_t *np_, size_t *ns_)
+{
+    tg_sqp_carve3(L, pbase, pbase, sbase, W, np_, ns_, 0);
+}
+
+// scratch needed by the line-search stage alone: cf + the obstacle scratch (carved like the full scratch so that
+// the same TgSqpWs works; u..hw are unused there and left dangling inside the small block)
+TG_HD size_t tg_sqp_ls_scratch_doubles(const TgLayout &L) { return (size_t)L.m + 1 + tg_scratch_doubles(L); }
+TG_HD size_t tg_sqp_prefix_doubles(const TgLayout &L) { size_t a, b, c; tg_sqp_carve3(L, 0, 0, 0, 0, &a, &b, &c); return c; }
 
 TG_HD size_t tg_sqp_persistent_doubles(const TgLayout &L) { size_t a, b; tg_sqp_carve2(L, 0, 0, 0, &a, &b); return a; }
 TG_HD size_t tg_sqp_scratch_doubles(const TgLayout &L) { size_t a, b; tg_sqp_carve2(L, 0, 0, 0, &a, &b); return b; }
