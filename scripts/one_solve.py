@@ -14,7 +14,8 @@ for r in range(reps):
     s.record(); out = tgb.solve(bt.spec, par, x, buffers=bufs); e.record(); torch.cuda.synchronize()
     print("solve %d: %.1f ms, status0 %.3f mean nit %.1f" % (r, s.elapsed_time(e), (out["status"] == 0).float().mean().item(), out["nit"].float().mean().item()))
 xe = torch.from_numpy(syn.evaluation_points(bt)).to(dev)
-for r in range(reps):
+o = tgb.evaluate(bt.spec, par, xe); torch.cuda.synchronize()
+for r in range(reps + 1):
     s = torch.cuda.Event(enable_timing=True); e = torch.cuda.Event(enable_timing=True)
-    s.record(); o = tgb.evaluate(bt.spec, par, xe); e.record(); torch.cuda.synchronize()
-    print("eval %d: %.3f ms" % (r, s.elapsed_time(e)))
+    s.record(); tgb.evaluate(bt.spec, par, xe, out=o); e.record(); torch.cuda.synchronize()
+    print("eval %d: %.3f ms  (%.1f M evaluations/s)" % (r, s.elapsed_time(e), B / s.elapsed_time(e) / 1e3))
