@@ -205,13 +205,14 @@ static int tg_plan_solve(const TgShape &S, int B, TgSolvePlan *P)
     return 0;
 }
 
+static size_t tg_lists_bytes(int chunk);
 extern "C" size_t tg_solve_workspace_bytes(const int *spec, int B)
 {
     TgShape S;
     TgSolvePlan P;
     if (tg_make_shape(spec, &S) || tg_plan_solve(S, B, &P)) return 0;
-    const size_t need = P.global_bytes > P.phased_bytes ? P.global_bytes : P.phased_bytes;
-    return need + 256;     // + counters
+    const size_t phased = P.phased_bytes + tg_lists_bytes(P.chunk);
+    return (P.global_bytes > phased ? P.global_bytes : phased) + TG_ROUNDCTL_BYTES;
 }
 
 #define TG_LAUNCH(call, what)                                                   \
@@ -221,28 +222,38 @@ extern "C" size_t tg_solve_workspace_bytes(const int *spec, int B)
         if (e_ != cudaSuccess) return tg_fail(100 + (int)e_, what, e_);         \
     } while (0)
 
+// device bookkeeping in front of the per-problem state: [TgRoundCtl | list0[chunk] | list1[chunk]], 256-byte aligned
+static size_t tg_lists_bytes(int chunk) { return (((size_t)2 * chunk * sizeof(int)) + 255) & ~(size_t)255; }
+
 static int tg_solve_phased(const TgShape &S, const TgSolvePlan &P, int B, const double *par, double *x, double *f,
-                           int *status, int *nit, int *violation, int maxiter, double ftol, int flags, int *counters,
-                           double *pws, cudaStream_t st)
+                           int *status, int *nit, int *violation, int maxiter, double ftol, int flags, void *workspace,
+                           cudaStream_t st)
 {
     const TgLayout &L = S.L;
+    TgRoundCtl *rc = (TgRoundCtl *)workspace;
+    int *lists[2] = {(int *)((char *)workspace + TG_ROUNDCTL_BYTES), (int *)((char *)workspace + TG_ROUNDCTL_BYTES) + P.chunk};
+    double *pws = (double *)((char *)workspace + TG_ROUNDCTL_BYTES + tg_lists_bytes(P.chunk));
     for (int lo = 0; lo < B; lo += P.chunk) {
         const int nb = B - lo < P.chunk ? B - lo : P.chunk;
         const double *cpar = par + (size_t)lo * L.P;
         double *cx = x + (size_t)lo * L.n;
-        TG_CUDA(cudaMemsetAsync(counters, 0, 256, st));
-        TG_LAUNCH(tg_launch_begin_g32(S, nb, cx, pws, P.np, maxiter, ftol, flags, st), "tg_sqp_begin_kernel");
+        TG_CUDA(cudaMemsetAsync(rc, 0, TG_ROUNDCTL_BYTES, st));
+        TG_LAUNCH(tg_launch_begin_g32(S, nb, cx, pws, P.np, maxiter, ftol, flags, rc, lists[0], st), "tg_sqp_begin_kernel");
         int done = 0;
-        // each round = one SLSQP major iteration of every unfinished problem; maxiter + 1 rounds finish everything
+        // each round = one SLSQP major iteration of every unfinished problem; maxiter + 1 rounds finish everything.
+        // Round r works through list r & 1; the QP stage builds the other list from the problems still running.
         for (int round = 0; round <= maxiter + 1 && done < nb; round++) {
-            TG_LAUNCH(TG_DISPATCH(P.gs_ls, tg_launch_ls_g8(S, nb, cpar, pws, P.np, P.smem_ls, st),
-                                  tg_launch_ls_g16(S, nb, cpar, pws, P.np, P.smem_ls, st),
-                                  tg_launch_ls_g32(S, nb, cpar, pws, P.np, P.smem_ls, st)), "tg_sqp_ls_kernel");
-            TG_LAUNCH(TG_DISPATCH(P.gs_qp, tg_launch_qp_g8(S, nb, pws, P.np, P.staged, P.smem_qp, counters, st),
-                                  tg_launch_qp_g16(S, nb, pws, P.np, P.staged, P.smem_qp, counters, st),
-                                  tg_launch_qp_g32(S, nb, pws, P.np, P.staged, P.smem_qp, counters, st)), "tg_sqp_qp_kernel");
+            const int par_ = round & 1;
+            TG_LAUNCH(TG_DISPATCH(P.gs_ls, tg_launch_ls_g8(S, nb, cpar, pws, P.np, P.smem_ls, rc, lists[par_], par_, g_sm_count, st),
+                                  tg_launch_ls_g16(S, nb, cpar, pws, P.np, P.smem_ls, rc, lists[par_], par_, g_sm_count, st),
+                                  tg_launch_ls_g32(S, nb, cpar, pws, P.np, P.smem_ls, rc, lists[par_], par_, g_sm_count, st)),
+                      "tg_sqp_ls_kernel");
+            TG_LAUNCH(TG_DISPATCH(P.gs_qp, tg_launch_qp_g8(S, nb, pws, P.np, P.staged, P.smem_qp, rc, lists[par_], lists[par_ ^ 1], par_, g_sm_count, st),
+                                  tg_launch_qp_g16(S, nb, pws, P.np, P.staged, P.smem_qp, rc, lists[par_], lists[par_ ^ 1], par_, g_sm_count, st),
+                                  tg_launch_qp_g32(S, nb, pws, P.np, P.staged, P.smem_qp, rc, lists[par_], lists[par_ ^ 1], par_, g_sm_count, st)),
+                      "tg_sqp_qp_kernel");
             if ((round & 7) == 7) {      // poll the number of finished problems
-                TG_CUDA(cudaMemcpyAsync(&done, counters, sizeof(int), cudaMemcpyDeviceToHost, st));
+                TG_CUDA(cudaMemcpyAsync(&done, &rc->done, sizeof(int), cudaMemcpyDeviceToHost, st));
                 TG_CUDA(cudaStreamSynchronize(st));
             }
         }
@@ -264,7 +275,8 @@ extern "C" int tg_solve_batch(const int *spec, int B, const double *par, double 
     if (B <= 0) return 0;
     if ((rc = tg_plan_solve(S, B, &P))) return rc;
     if (S.L.n > 62) return tg_fail(3, "more than 62 optimisation variables are not supported by the solve kernel");
-    const size_t need = (P.global_bytes > P.phased_bytes ? P.global_bytes : P.phased_bytes) + 256;
+    const size_t phased = P.phased_bytes + tg_lists_bytes(P.chunk);
+    const size_t need = (P.global_bytes > phased ? P.global_bytes : phased) + TG_ROUNDCTL_BYTES;
     if (!workspace || workspace_bytes < need) return tg_fail(4, "workspace too small (see tg_solve_workspace_bytes)");
     int *counters = (int *)workspace;
     double *gws = (double *)((char *)workspace + 256);
@@ -276,7 +288,7 @@ extern "C" int tg_solve_batch(const int *spec, int B, const double *par, double 
                                       counters, st), "tg_solve_kernel");
         return 0;
     }
-    return tg_solve_phased(S, P, B, par, x, f, status, nit, violation, maxiter, ftol, flags, counters, gws, st);
+    return tg_solve_phased(S, P, B, par, x, f, status, nit, violation, maxiter, ftol, flags, workspace, st);
 }
 
 // ---------------------------------------------------------------------------

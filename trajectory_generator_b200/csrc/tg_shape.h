@@ -10,14 +10,13 @@ struct TgShape {
     TgLayout L;
 };
 
-// launch description of the lock-step solve stages
-struct TgStageLaunch {
-    int B;                // problems in this chunk
-    size_t np;            // persistent doubles per problem
-    int staged_qp;        // QP stage: persistent state staged through shared memory
-    size_t smem_ls, smem_qp;
-    int threads;          // threads per CTA
+// round bookkeeping of the lock-step solve (device memory).  Round r works through list[r & 1] (count[r & 1]
+// problem indices, handed out through the head_* cursors) and the QP stage appends the problems that are not
+// finished to the other list; `done` counts finished problems (polled by the host).
+struct TgRoundCtl {
+    int count[2], head_ls[2], head_qp[2], done;
 };
+#define TG_ROUNDCTL_BYTES 256
 
 #define TG_DECLARE_VARIANT(SFX)                                                                                           \
     cudaError_t tg_launch_eval##SFX(const TgShape &S, int B, const double *par, const double *x, double *f, double *g,    \
@@ -26,11 +25,11 @@ struct TgStageLaunch {
                                       cudaStream_t st);                                                                   \
     size_t tg_eval_smem##SFX(const TgShape &S);                                                                           \
     cudaError_t tg_launch_begin##SFX(const TgShape &S, int B, const double *x, double *pws, size_t np, int maxiter,       \
-                                     double ftol, int flags, cudaStream_t st);                                            \
+                                     double ftol, int flags, TgRoundCtl *rc, int *list0, cudaStream_t st);                \
     cudaError_t tg_launch_ls##SFX(const TgShape &S, int B, const double *par, double *pws, size_t np, size_t smem,        \
-                                  cudaStream_t st);                                                                       \
-    cudaError_t tg_launch_qp##SFX(const TgShape &S, int B, double *pws, size_t np, int staged, size_t smem, int *counters, \
-                                  cudaStream_t st);                                                                       \
+                                  TgRoundCtl *rc, const int *list, int parity, int sm_count, cudaStream_t st);            \
+    cudaError_t tg_launch_qp##SFX(const TgShape &S, int B, double *pws, size_t np, int staged, size_t smem,               \
+                                  TgRoundCtl *rc, const int *list, int *next, int parity, int sm_count, cudaStream_t st); \
     size_t tg_ls_smem##SFX(const TgShape &S);                                                                             \
     size_t tg_qp_smem##SFX(const TgShape &S, int staged);                                                                 \
     cudaError_t tg_launch_finish##SFX(const TgShape &S, int B, const double *pws, size_t np, double *x, double *f,        \
