@@ -26,18 +26,21 @@ LAYOUT_FIELDS = ("d N nint n ia is0 is1 it0 nws niw meq mineq m r_start n_start 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC"]
 # translation units: the host API (+ legacy single-problem kernels) and one unit per (kernel family, lanes per problem)
-UNITS = ["tg_api.cu"] + ["tg_%s_g%d.cu" % (fam, gs) for fam in ("eval", "solve") for gs in (8, 16, 32)]
+UNITS = ["tg_api.cu", "tg_solve_fused.cu"] + ["tg_%s_g%d.cu" % (fam, gs) for fam in ("eval", "solve") for gs in (8, 16, 32)]
 HEADERS = ["tg_sqp.h", "tg_eval.h", "tg_spec.h", "tg_shape.h", "tg_kernels_eval.inc", "tg_kernels_solve.inc"]
 
 
-def build_native(force=False, verbose=False):
+def build_native(force=False, verbose=False, variant=None, extra_flags=()):
     """Compile csrc/*.cu for sm_100a into lib/libTrajectoryConstraints.so (nvcc cross-compiles without a GPU).
-    Units are compiled in parallel into lib/obj/ and linked into one shared library."""
+    Units are compiled in parallel into lib/obj/ and linked into one shared library.
+    `variant` (tuning experiments only): build lib/variants/<variant>.so with `extra_flags`; select it at run time
+    with the environment variable TG_LIB=<path>."""
     from concurrent.futures import ThreadPoolExecutor
     deps = [os.path.join(CSRC, f) for f in HEADERS]
     deps.append(os.path.join(os.path.dirname(HERE), "include", "trajectory_generator_b200.h"))
-    objdir = os.path.join(HERE, "lib", "obj")
+    objdir = os.path.join(HERE, "lib", "obj" if not variant else os.path.join("variants", variant + "_obj"))
     os.makedirs(objdir, exist_ok=True)
+    lib_path = LIB_PATH if not variant else os.path.join(HERE, "lib", "variants", variant + ".so")
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     newest_dep = max(os.path.getmtime(d) for d in deps)
 
@@ -46,7 +49,7 @@ def build_native(force=False, verbose=False):
         obj = os.path.join(objdir, unit.replace(".cu", ".o"))
         if not force and os.path.exists(obj) and os.path.getmtime(obj) >= max(newest_dep, os.path.getmtime(src)):
             return obj, False, ""
-        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, src]
+        cmd = [nvcc] + NVCC_FLAGS + list(extra_flags) + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, src]
         proc = subprocess.run(cmd, capture_output=True, text=True)
         if proc.returncode != 0:
             raise RuntimeError("nvcc failed:\n%s\n%s" % (" ".join(cmd), proc.stderr))
@@ -58,12 +61,12 @@ def build_native(force=False, verbose=False):
         for _, _, log in results:
             print(log)
     objs = [r[0] for r in results]
-    if force or any(r[1] for r in results) or not os.path.exists(LIB_PATH):
-        cmd = [nvcc, "-shared", "-o", LIB_PATH] + objs
+    if force or any(r[1] for r in results) or not os.path.exists(lib_path):
+        cmd = [nvcc, "-shared", "-o", lib_path] + objs
         proc = subprocess.run(cmd, capture_output=True, text=True)
         if proc.returncode != 0:
             raise RuntimeError("link failed:\n%s\n%s" % (" ".join(cmd), proc.stderr))
-    return LIB_PATH
+    return lib_path
 
 
 _LIB = None
@@ -75,10 +78,11 @@ def lib():
     """The loaded CUDA library; raises if it has not been built (no fallback)."""
     global _LIB
     if _LIB is None:
-        if not os.path.exists(LIB_PATH):
+        path = os.environ.get("TG_LIB", LIB_PATH)         # TG_LIB: a tuning variant built by build_native(variant=...)
+        if not os.path.exists(path):
             raise RuntimeError("CUDA library %s is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
-                               "(there is no CPU fallback)" % LIB_PATH)
-        L = ctypes.CDLL(LIB_PATH)
+                               "(there is no CPU fallback)" % path)
+        L = ctypes.CDLL(path)
         L.tg_spec_count.restype = ctypes.c_int
         L.tg_layout.argtypes = [_I32, _I32, ctypes.c_int]
         L.tg_layout.restype = ctypes.c_int

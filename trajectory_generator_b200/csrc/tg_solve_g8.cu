@@ -1,4 +1,8 @@
 // M2 solve kernels, 8 lanes per problem (see tg_kernels_solve.inc)
 #define TG_GS 8
+// the lock-step kernels run every warp through the same code at the same time: the block evaluators are inlined
+#ifndef TG_NO_INLINE_LS
+#define TG_INLINE_ALL
+#endif
 #define TG_SFX _g8
 #include "tg_kernels_solve.inc"

@@ -48,11 +48,20 @@ struct TgSqpWs {
     // persistent
     double *x, *xl, *xu, *g, *s, *x0, *gl, *c, *mu, *r, *Lm, *Dd, *A;
     // scratch
-    double *u, *v, *w, *cf, *Jq, *R, *z, *dq, *rq, *np, *uq, *xq, *hw, *scratch;
+    double *u, *v, *w, *cf, *Jq, *R, *z, *dq, *rq, *np, *uq, *xq, *hw, *rdi, *scratch;
     int *act, *iact;
 };
 
 TG_HD int tg_odd(int v) { return v | 1; }
+
+// The QP-stage functions are inlined into the lock-step QP kernel (one call site each; with the workspace carved
+// from the kernel's shared array the compiler then knows the address space of every access).  The fused kernel's
+// translation unit defines TG_SQP_NOINLINE (instruction-cache footprint).
+#if defined(__CUDACC__) && !defined(TG_SQP_NOINLINE)
+#define TG_QFN static __host__ __device__ __forceinline__
+#else
+#define TG_QFN TG_FN
+#endif
 
 // Carves the per-problem state.  The persistent block is [ctl | x xl xu g s x0 | c mu | gl r Lm Dd | A]; its first
 // `npre` doubles (everything the line-search stage touches except A) may be staged at `prefix` while the rest
@@ -65,7 +74,7 @@ TG_HD void tg_sqp_carve3(const TgLayout &L, double *prefix, double *pbase, doubl
     w.n = n; w.n1 = n1; w.m = m; w.lda = tg_odd(m > 0 ? m : 1); w.ldq = tg_odd(n1); w.nc = m + 2 * n1;
     size_t o = 0;
     double *base = prefix;
-#define TG_TAKE(field, count) w.field = base ? base + o : 0; o += (size_t)(count)
+#define TG_TAKE(field, count) w.field = base + o; o += (size_t)(count)
     w.ctl = (TgSqpCtl *)base; o += TG_CTL_DOUBLES;
     TG_TAKE(x, n1); TG_TAKE(xl, n1); TG_TAKE(xu, n1); TG_TAKE(g, n1); TG_TAKE(s, n1); TG_TAKE(x0, n1);
     TG_TAKE(c, m + 1); TG_TAKE(mu, m + 1);
@@ -80,7 +89,8 @@ TG_HD void tg_sqp_carve3(const TgLayout &L, double *prefix, double *pbase, doubl
     TG_TAKE(u, n1); TG_TAKE(v, n1); TG_TAKE(w, n1);
     TG_TAKE(Jq, w.ldq * n1); TG_TAKE(R, w.ldq * n1);
     TG_TAKE(z, n1); TG_TAKE(dq, n1); TG_TAKE(rq, n1); TG_TAKE(np, n1); TG_TAKE(uq, n1 + 1); TG_TAKE(xq, n1); TG_TAKE(hw, n1);
-    double *ints = base ? base + o : 0; o += (size_t)((n1 + 1 + w.nc + 1) / 2 + 1);
+    TG_TAKE(rdi, n1);
+    double *ints = base + o; o += (size_t)((n1 + 1 + w.nc + 1) / 2 + 1);
     w.act = (int *)ints; w.iact = w.act + n1 + 1;
 #undef TG_TAKE
     if (ns_) *ns_ = o;
@@ -117,7 +127,7 @@ TG_HD bool tg_finite(double v) { return v - v == 0; }
 // Powell, as used by SLSQP's LDL routine).  Lm: unit lower factor, column i at
 // Lm[i*n + j] (j > i); Dd: diagonal.  z is destroyed; w is scratch.
 // ---------------------------------------------------------------------------
-TG_FN void tg_ldl_update(int n, double sigma, double *z, double *Lm, double *Dd, double *w)
+TG_QFN void tg_ldl_update(int n, double sigma, double *z, double *Lm, double *Dd, double *w)
 {
     const int lane = TG_LANE();
     if (sigma == 0) return;
@@ -152,39 +162,40 @@ TG_FN void tg_ldl_update(int n, double sigma, double *z, double *Lm, double *Dd,
         const double delta = vv / di;
         const double tp = sigma < 0 ? w[i] : t + delta * vv;
         const double alpha = tp / t;
-        TG_SYNC();
-        if (lane == 0) Dd[i] = alpha * di;
-        if (i == n - 1) break;
-        const double beta = delta / tp;
-        if (alpha > 4) {
-            const double gamma = t / tp;
-            #pragma unroll 1
-            for (int j = i + 1 + lane; j < n; j += TG_NL) {
-                const double uu = Lm[i * n + j];
-                Lm[i * n + j] = gamma * uu + beta * z[j];
-                z[j] -= vv * uu;
-            }
-        } else {
-            #pragma unroll 1
-            for (int j = i + 1 + lane; j < n; j += TG_NL) {
-                z[j] -= vv * Lm[i * n + j];
-                Lm[i * n + j] += beta * z[j];
+        const double dnew = alpha * di;            // written after the step's barrier (every lane has read Dd[i] by then)
+        if (i < n - 1) {
+            const double beta = delta / tp;
+            if (alpha > 4) {
+                const double gamma = t / tp;
+                #pragma unroll 1
+                for (int j = i + 1 + lane; j < n; j += TG_NL) {
+                    const double uu = Lm[i * n + j];
+                    Lm[i * n + j] = gamma * uu + beta * z[j];
+                    z[j] -= vv * uu;
+                }
+            } else {
+                #pragma unroll 1
+                for (int j = i + 1 + lane; j < n; j += TG_NL) {
+                    z[j] -= vv * Lm[i * n + j];
+                    Lm[i * n + j] += beta * z[j];
+                }
             }
         }
         t = tp;
         TG_SYNC();
+        if (lane == 0) Dd[i] = dnew;
     }
     TG_SYNC();
 }
 
 // out = L D L^T s  (tmp: n scratch)
-TG_FN void tg_ldl_apply(int n, const double *Lm, const double *Dd, const double *s, double *tmp, double *out)
+TG_QFN void tg_ldl_apply(int n, const double *Lm, const double *Dd, const double *s, double *tmp, double *out)
 {
     const int lane = TG_LANE();
     #pragma unroll 1
     for (int i = lane; i < n; i += TG_NL) {
         double h = s[i];
-        #pragma unroll 1
+        #pragma unroll 4
         for (int j = i + 1; j < n; j++) h += Lm[i * n + j] * s[j];
         tmp[i] = Dd[i] * h;
     }
@@ -192,7 +203,7 @@ TG_FN void tg_ldl_apply(int n, const double *Lm, const double *Dd, const double 
     #pragma unroll 1
     for (int i = lane; i < n; i += TG_NL) {
         double h = tmp[i];
-        #pragma unroll 1
+        #pragma unroll 4
         for (int j = 0; j < i; j++) h += Lm[j * n + i] * tmp[j];
         out[i] = h;
     }
@@ -239,7 +250,7 @@ TG_HD double tg_qp_value(const TgSqpWs &W, int nq, int p)
 }
 
 // d = J' np ; z = J2 d2 ; rq = R^-1 d1 ; returns |d2|^2 (= z.np) and |d|^2
-TG_FN void tg_qp_directions(const TgSqpWs &W, int nq, int iq, double &d2n, double &dn)
+TG_QFN void tg_qp_directions(const TgSqpWs &W, int nq, int iq, double &d2n, double &dn)
 {
     const int lane = TG_LANE(), ld = W.ldq;
     double a = 0, b = 0;
@@ -247,7 +258,7 @@ TG_FN void tg_qp_directions(const TgSqpWs &W, int nq, int iq, double &d2n, doubl
     for (int k = lane; k < nq; k += TG_NL) {
         double h = 0;
         const double *col = W.Jq + k * ld;
-        #pragma unroll 1
+        #pragma unroll 4
         for (int i = 0; i < nq; i++) h += col[i] * W.np[i];
         W.dq[k] = h;
         W.hw[k] = h;
@@ -260,15 +271,14 @@ TG_FN void tg_qp_directions(const TgSqpWs &W, int nq, int iq, double &d2n, doubl
     #pragma unroll 1
     for (int i = lane; i < nq; i += TG_NL) {
         double h = 0;
-        #pragma unroll 1
+        #pragma unroll 4
         for (int k = iq; k < nq; k++) h += W.Jq[k * ld + i] * W.dq[k];
         W.z[i] = h;
     }
-    // back substitution R rq = d1 (column oriented; hw holds the running right-hand side)
+    // back substitution R rq = d1 (column oriented; hw holds the running right-hand side, rdi = 1 / diag R)
     #pragma unroll 1
     for (int j = iq - 1; j >= 0; j--) {
-        const double rj = W.hw[j] / W.R[j * ld + j];
-        TG_SYNC();
+        const double rj = W.hw[j] * W.rdi[j];
         if (lane == 0) W.rq[j] = rj;
         #pragma unroll 1
         for (int k = lane; k < j; k += TG_NL) W.hw[k] -= W.R[j * ld + k] * rj;
@@ -277,38 +287,39 @@ TG_FN void tg_qp_directions(const TgSqpWs &W, int nq, int iq, double &d2n, doubl
     TG_SYNC();
 }
 
-// append constraint with J'np = dq to the factorisation (Householder on dq[iq..])
-TG_FN void tg_qp_add(const TgSqpWs &W, int nq, int iq)
+// append the constraint with J'np = dq to the factorisation: Householder reflection of dq[iq..] onto e_iq applied
+// to the columns iq.. of J.  J2 w = z - sigma J[:, iq] with z = J2 d2 from tg_qp_directions (d2n = |d2|^2).
+TG_QFN void tg_qp_add(const TgSqpWs &W, int nq, int iq, double d2n)
 {
     const int lane = TG_LANE(), ld = W.ldq;
-    double nn = 0;
-    #pragma unroll 1
-    for (int k = iq + lane; k < nq; k += TG_NL) nn += W.dq[k] * W.dq[k];
-    nn = tg_wsum(nn);
     const double d0 = W.dq[iq];
-    const double sigma = d0 > 0 ? -sqrt(nn) : sqrt(nn);
-    // w = d2 - sigma e1 ;  w'w = 2 (nn - sigma d0)
-    const double ww = 2 * (nn - sigma * d0);
+    const double sigma = d0 > 0 ? -sqrt(d2n) : sqrt(d2n);
+    // w = d2 - sigma e1 ;  w'w = 2 (|d2|^2 - sigma d0)
+    const double ww = 2 * (d2n - sigma * d0);
+    const double w0 = d0 - sigma;
     TG_SYNC();
     if (ww > 0) {
+        const double sc = 2 / ww;
         #pragma unroll 1
         for (int i = lane; i < nq; i += TG_NL) {
-            double t = 0;
-            #pragma unroll 1
-            for (int k = iq; k < nq; k++) t += W.Jq[k * ld + i] * (k == iq ? d0 - sigma : W.dq[k]);
-            t *= 2 / ww;
-            #pragma unroll 1
-            for (int k = iq; k < nq; k++) W.Jq[k * ld + i] -= t * (k == iq ? d0 - sigma : W.dq[k]);
+            const double t = (W.z[i] - sigma * W.Jq[iq * ld + i]) * sc;
+            W.Jq[iq * ld + i] -= t * w0;
+            #pragma unroll 4
+            for (int k = iq + 1; k < nq; k++) W.Jq[k * ld + i] -= t * W.dq[k];
         }
     }
     #pragma unroll 1
     for (int k = lane; k < iq; k += TG_NL) W.R[iq * ld + k] = W.dq[k];
-    if (lane == 0) W.R[iq * ld + iq] = ww > 0 ? sigma : d0;
+    if (lane == 0) {
+        const double rd = ww > 0 ? sigma : d0;
+        W.R[iq * ld + iq] = rd;
+        W.rdi[iq] = 1 / rd;
+    }
     TG_SYNC();
 }
 
 // remove the constraint at position l of the active list
-TG_FN void tg_qp_drop(const TgSqpWs &W, int nq, int &iq, int l)
+TG_QFN void tg_qp_drop(const TgSqpWs &W, int nq, int &iq, int l)
 {
     const int lane = TG_LANE(), ld = W.ldq;
     if (lane == 0) W.iact[W.act[l]] = 0;
@@ -325,9 +336,9 @@ TG_FN void tg_qp_drop(const TgSqpWs &W, int nq, int &iq, int l)
         double cc = W.R[j * ld + j], ss = W.R[j * ld + j + 1];
         const double h = sqrt(cc * cc + ss * ss);
         TG_SYNC();
-        if (h == 0) continue;
+        if (h == 0) { if (lane == 0) W.rdi[j] = INFINITY; continue; }
         cc /= h; ss /= h;
-        if (lane == 0) { W.R[j * ld + j] = h; W.R[j * ld + j + 1] = 0; }
+        if (lane == 0) { W.R[j * ld + j] = h; W.R[j * ld + j + 1] = 0; W.rdi[j] = 1 / h; }
         #pragma unroll 1
         for (int k = j + 1 + lane; k < iq; k += TG_NL) {
             const double t1 = W.R[k * ld + j], t2 = W.R[k * ld + j + 1];
@@ -345,28 +356,26 @@ TG_FN void tg_qp_drop(const TgSqpWs &W, int nq, int &iq, int l)
     TG_SYNC();
 }
 
-TG_FN int tg_qp_solve(const TgSqpWs &W, int nq, int meq, double rho)
+TG_QFN int tg_qp_solve(const TgSqpWs &W, int nq, int meq, double rho)
 {
     const int lane = TG_LANE(), n = W.n, ld = W.ldq, m = W.m;
     const int nc = m + 2 * W.n1;
     const double EPS_DEP = 1e-26;     // |d2|^2 <= EPS_DEP |d|^2 : normal lies in the span of the active ones
-    // ---- J = L^-T D^-1/2 (upper triangular), augmented entry 1/sqrt(rho)
+    // ---- J = L^-T D^-1/2 (upper triangular), augmented entry 1/rho
     #pragma unroll 1
     for (int k = lane; k < nq; k += TG_NL) {
         double *col = W.Jq + k * ld;
-        #pragma unroll 1
         for (int i = 0; i < nq; i++) col[i] = 0;
         if (k < n) {
             col[k] = 1;
             #pragma unroll 1
             for (int i = k - 1; i >= 0; i--) {
                 double h = 0;
-                #pragma unroll 1
+                #pragma unroll 4
                 for (int j = i + 1; j <= k; j++) h += W.Lm[i * n + j] * col[j];
                 col[i] = -h;
             }
             const double sc = 1 / sqrt(W.Dd[k]);
-            #pragma unroll 1
             for (int i = 0; i <= k; i++) col[i] *= sc;
         } else col[k] = 1 / rho;      // SLSQP's LSQ puts rho itself (not its root) on the diagonal of E: penalty rho^2/2 delta^2
     }
@@ -377,7 +386,7 @@ TG_FN int tg_qp_solve(const TgSqpWs &W, int nq, int meq, double rho)
     #pragma unroll 1
     for (int k = lane; k < nq; k += TG_NL) {
         double h = 0;
-        #pragma unroll 1
+        #pragma unroll 4
         for (int i = 0; i < nq; i++) h += W.Jq[k * ld + i] * W.g[i];
         W.dq[k] = h;
     }
@@ -385,63 +394,50 @@ TG_FN int tg_qp_solve(const TgSqpWs &W, int nq, int meq, double rho)
     #pragma unroll 1
     for (int i = lane; i < nq; i += TG_NL) {
         double h = 0;
-        #pragma unroll 1
+        #pragma unroll 4
         for (int k = 0; k < nq; k++) h += W.Jq[k * ld + i] * W.dq[k];
         W.xq[i] = -h;
     }
     TG_SYNC();
     int iq = 0;
     double d2n, dn;
-    // ---- equality rows, in order
-    #pragma unroll 1
-    for (int p = 0; p < meq; p++) {
-        tg_qp_normal(W, nq, p, W.np);
-        tg_qp_directions(W, nq, iq, d2n, dn);
-        if (!(d2n > EPS_DEP * dn)) return 6;
-        const double sv = tg_qp_value(W, nq, p);
-        const double t2 = -sv / d2n;
-        #pragma unroll 1
-        for (int i = lane; i < nq; i += TG_NL) W.xq[i] += t2 * W.z[i];
-        #pragma unroll 1
-        for (int k = lane; k < iq; k += TG_NL) W.uq[k] -= t2 * W.rq[k];
-        if (lane == 0) { W.uq[iq] = t2; W.act[iq] = p; W.iact[p] = 1; }
-        TG_SYNC();
-        tg_qp_add(W, nq, iq);
-        iq++;
-    }
-    // ---- inequality rows and bounds
+    // ---- the equality rows in order (outer steps 0 .. meq-1), then the most violated inequality row or bound
     const int itmax = 10 * (nc + nq) + 100;
     #pragma unroll 1
-    for (int it = 0; it < itmax; it++) {
-        // most violated inactive constraint
-        double best = 0; int ip = 0x7fffffff;
-        #pragma unroll 1
-        for (int p = meq + lane; p < nc; p += TG_NL) {
-            if (W.iact[p]) continue;
-            double sv, tol;
-            if (p < m) {
-                double h = 0, sc = fabs(W.c[p]);
-                #pragma unroll 1
-                for (int i = 0; i < nq; i++) { const double t = W.A[i * W.lda + p] * W.xq[i]; h += t; sc += fabs(t); }
-                sv = h + W.c[p];
-                tol = 1e-13 * sc;
-            } else {
-                const int q = p - m;
-                const int i = q < W.n1 ? q : q - W.n1;
-                if (i >= nq) continue;
-                const double bnd = q < W.n1 ? W.u[i] : W.v[i];
-                if (!tg_finite(bnd)) continue;
-                sv = q < W.n1 ? W.xq[i] - bnd : bnd - W.xq[i];
-                tol = 1e-13 * (fabs(bnd) + fabs(W.xq[i]));
-            }
-            if (sv < -tol && sv < best) { best = sv; ip = p; }
-        }
-        tg_wargmin(best, ip);
-        if (ip == 0x7fffffff) {
+    for (int it = 0; it < itmax + meq; it++) {
+        const bool eq = it < meq;
+        int ip = it;
+        if (!eq) {
+            double best = 0;
+            ip = 0x7fffffff;
             #pragma unroll 1
-            for (int k = lane; k < iq; k += TG_NL) W.r[W.act[k]] = W.uq[k];
-            TG_SYNC();
-            return TG_QP_OK;
+            for (int p = meq + lane; p < nc; p += TG_NL) {
+                if (W.iact[p]) continue;
+                double sv, tol;
+                if (p < m) {
+                    double h = 0, sc = fabs(W.c[p]);
+                    #pragma unroll 4
+                    for (int i = 0; i < nq; i++) { const double t = W.A[i * W.lda + p] * W.xq[i]; h += t; sc += fabs(t); }
+                    sv = h + W.c[p];
+                    tol = 1e-13 * sc;
+                } else {
+                    const int q = p - m;
+                    const int i = q < W.n1 ? q : q - W.n1;
+                    if (i >= nq) continue;
+                    const double bnd = q < W.n1 ? W.u[i] : W.v[i];
+                    if (!tg_finite(bnd)) continue;
+                    sv = q < W.n1 ? W.xq[i] - bnd : bnd - W.xq[i];
+                    tol = 1e-13 * (fabs(bnd) + fabs(W.xq[i]));
+                }
+                if (sv < -tol && sv < best) { best = sv; ip = p; }
+            }
+            tg_wargmin(best, ip);
+            if (ip == 0x7fffffff) {
+                #pragma unroll 1
+                for (int k = lane; k < iq; k += TG_NL) W.r[W.act[k]] = W.uq[k];
+                TG_SYNC();
+                return TG_QP_OK;
+            }
         }
         tg_qp_normal(W, nq, ip, W.np);
         double uip = 0;
@@ -451,37 +447,40 @@ TG_FN int tg_qp_solve(const TgSqpWs &W, int nq, int meq, double rho)
             tg_qp_directions(W, nq, iq, d2n, dn);
             // dual step length: active inequalities whose multiplier would turn negative
             double t1 = INFINITY; int l = 0x7fffffff;
-            #pragma unroll 1
-            for (int k = lane; k < iq; k += TG_NL)
-                if (W.act[k] >= meq && W.rq[k] > 0) {
-                    const double t = W.uq[k] / W.rq[k];
-                    if (t < t1) { t1 = t; l = k; }
-                }
-            tg_wargmin(t1, l);
-            const double t2 = d2n > EPS_DEP * dn ? -sv / d2n : INFINITY;
+            if (!eq) {
+                #pragma unroll 1
+                for (int k = lane; k < iq; k += TG_NL)
+                    if (W.act[k] >= meq && W.rq[k] > 0) {
+                        const double t = W.uq[k] / W.rq[k];
+                        if (t < t1) { t1 = t; l = k; }
+                    }
+                tg_wargmin(t1, l);
+            }
+            const bool indep = d2n > EPS_DEP * dn;
+            if (eq && !indep) return 6;
+            const double t2 = indep ? -sv / d2n : INFINITY;
             const double t = t1 < t2 ? t1 : t2;
             if (!(t < INFINITY)) return 4;
             #pragma unroll 1
             for (int k = lane; k < iq; k += TG_NL) W.uq[k] -= t * W.rq[k];
             uip += t;
-            if (!(t2 < INFINITY)) {
-                TG_SYNC();
-                tg_qp_drop(W, nq, iq, l);
-                continue;
-            }
-            #pragma unroll 1
-            for (int i = lane; i < nq; i += TG_NL) W.xq[i] += t * W.z[i];
+            const bool primal = t2 < INFINITY;
+            if (primal)
+                #pragma unroll 1
+                for (int i = lane; i < nq; i += TG_NL) W.xq[i] += t * W.z[i];
             TG_SYNC();
-            if (t2 <= t1) {
+            if (primal && t2 <= t1) {
                 if (lane == 0) { W.uq[iq] = uip; W.act[iq] = ip; W.iact[ip] = 1; }
                 TG_SYNC();
-                tg_qp_add(W, nq, iq);
+                tg_qp_add(W, nq, iq, d2n);
                 iq++;
                 break;
             }
             tg_qp_drop(W, nq, iq, l);
-            sv = tg_qp_value(W, nq, ip);
-            if (inner == itmax - 1) return 3;
+            if (primal) {
+                sv = tg_qp_value(W, nq, ip);
+                if (inner == itmax - 1) return 3;
+            }
         }
     }
     return 3;
@@ -633,7 +632,7 @@ TG_FN void tg_sqp_stage_ls(const TgLayout &L, const int *sp, const double *par, 
     TG_SYNC();
 }
 
-TG_FN void tg_sqp_stage_qp(const TgLayout &L, const TgSqpWs &W)
+TG_QFN void tg_sqp_stage_qp(const TgLayout &L, const TgSqpWs &W)
 {
     const int lane = TG_LANE(), n = L.n, m = L.m, meq = L.meq, n1 = W.n1;
     TgSqpCtl ctl = *W.ctl;
@@ -673,8 +672,9 @@ TG_FN void tg_sqp_stage_qp(const TgLayout &L, const TgSqpWs &W)
             TG_SYNC();
             if (h1 == 0 || h2 == 0) ctl.need_reset = 1;
             else {
-                tg_ldl_update(n, 1 / h1, W.u, W.Lm, W.Dd, W.w);
-                tg_ldl_update(n, -1 / h2, W.v, W.Lm, W.Dd, W.w);
+                #pragma unroll 1
+                for (int pass = 0; pass < 2; pass++)
+                    tg_ldl_update(n, pass == 0 ? 1 / h1 : -1 / h2, pass == 0 ? W.u : W.v, W.Lm, W.Dd, W.w);
             }
             ctl.state = TG_ST_QP;
         }
@@ -709,27 +709,30 @@ TG_FN void tg_sqp_stage_qp(const TgLayout &L, const TgSqpWs &W)
             for (int i = lane; i < n; i += TG_NL) { W.u[i] = W.xl[i] - W.x[i]; W.v[i] = W.xu[i] - W.x[i]; }
             TG_SYNC();
             ctl.h4 = 1;
-            int mode = tg_qp_solve(W, n, meq, 0.0);
             ctl.badlin = 0;
-            if (mode == 6 && n == meq) mode = 4;
-            if (mode == 4) {
-                // ---- augmented problem for an inconsistent linearisation
-                ctl.badlin = 1;
-                #pragma unroll 1
-                for (int j = lane; j < m; j += TG_NL) W.A[n * W.lda + j] = j < meq ? -W.c[j] : fmax(-W.c[j], 0.0);
-                if (lane == 0) { W.g[n] = 0; W.u[n] = 0; W.v[n] = 1; }
-                TG_SYNC();
-                double rho = 100;
-                #pragma unroll 1
-                for (int incons = 0;; incons++) {
-                    mode = tg_qp_solve(W, n1, meq, rho);
+            // first the QP itself; if its linearised constraints are inconsistent, the augmented problem with one
+            // slack variable (penalty 100, x10 per retry, at most 6 attempts)
+            int mode = 0, nq = n;
+            double rho = 0;
+            #pragma unroll 1
+            for (int attempt = 0; attempt < 7; attempt++) {
+                mode = tg_qp_solve(W, nq, meq, rho);
+                if (attempt == 0) {
+                    if (mode == 6 && n == meq) mode = 4;
+                    if (mode != 4) break;
+                    ctl.badlin = 1;
+                    #pragma unroll 1
+                    for (int j = lane; j < m; j += TG_NL) W.A[n * W.lda + j] = j < meq ? -W.c[j] : fmax(-W.c[j], 0.0);
+                    if (lane == 0) { W.g[n] = 0; W.u[n] = 0; W.v[n] = 1; }
+                    TG_SYNC();
+                    nq = n1; rho = 100;
+                } else {
                     if (mode != 4) break;
                     rho *= 10;
-                    if (incons + 1 > 5) break;
                 }
-                if (mode != TG_QP_OK) { ctl.status = mode; ctl.state = TG_ST_DONE; break; }
-                ctl.h4 = 1 - W.xq[n];
-            } else if (mode != TG_QP_OK) { ctl.status = mode; ctl.state = TG_ST_DONE; break; }
+            }
+            if (mode != TG_QP_OK) { ctl.status = mode; ctl.state = TG_ST_DONE; break; }
+            if (ctl.badlin) ctl.h4 = 1 - W.xq[n];
             // ---- gradient of the Lagrangian at the old point, merit weights
             #pragma unroll 1
             for (int i = lane; i < n; i += TG_NL) {
@@ -803,5 +806,31 @@ TG_FN void tg_sqp_solve(const TgLayout &L, const int *sp, const double *par, dou
         res->nfev = W.ctl->nfev; res->f = W.ctl->f;
     }
 }
+
+// the reference's is_violation: violation flags of the LAST constraint in its list, tolerance 10e-6
+// (TG/trajectory_generator.py:252-261, DS/constraint_function_data.py:12,45-48)
+TG_HD int tg_last_block_violation(const TgLayout &L, const double *c)
+{
+    int r0, r1, eq = 0;
+    if (L.n_obs) { r0 = L.r_obs; r1 = r0 + L.n_obs; }
+    else if (L.n_sfc) { r0 = L.r_sfcl; r1 = r0 + 2 * L.n_sfc; }
+    else if (L.n_turn) { r0 = L.r_turn; r1 = r0 + 1; }
+    else if (L.n_tan) { r0 = L.r_tanl; r1 = r0 + 2 * L.n_tan; }
+    else if (L.n_db) { r0 = L.r_db; r1 = r0 + L.n_db; }
+    else if (L.n_iwv) { r0 = L.r_iwv; r1 = r0 + L.n_iwv; eq = 1; }
+    else if (L.n_iwl) { r0 = L.r_iwl; r1 = r0 + L.n_iwl; eq = 1; }
+    else if (L.n_eder) { r0 = L.r_eder; r1 = r0 + L.n_eder; eq = 1; }
+    else if (L.n_sder) { r0 = L.r_sder; r1 = r0 + L.n_sder; eq = 1; }
+    else { r0 = L.r_end; r1 = r0 + L.n_end; eq = 1; }
+    int bad = 0;
+    #pragma unroll 1
+    for (int j = r0 + TG_LANE(); j < r1; j += TG_NL) {
+        const double v = c[j];
+        if (eq ? (fabs(v) > 10e-6) : (v < -10e-6)) bad = 1;
+        if (v != v) bad = 1;
+    }
+    return tg_any(bad);
+}
+
 
 #endif  // TG_SQP_H
