@@ -24,6 +24,10 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# dram__bytes_read.sum + dram__bytes_write.sum of one QP-stage launch (round 10, 65,536 problems) from the committed
+# `ncu --set full` captures (profiles/README.md); bytes per launch
+NCU_TRAFFIC = {}
+
 METRIC = "optimized_trajectories_per_sec"
 UNIT = "trajectories/s"
 L2_FLUSH_BYTES = 512 << 20
@@ -149,7 +153,7 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        sample = args.cpu_sample or min(256, max(32, 2 * cores))
+        sample = args.cpu_sample or max(64, 8 * cores)
         times = []
         for it in range(args.warmup + args.steps):
             if it < args.warmup and it > 0:
@@ -246,6 +250,21 @@ def main():
     status = bufs.status.cpu().numpy(); nit = bufs.nit.cpu().numpy()
     x_gpu = x.cpu().numpy()
 
+    # ---- per-kernel share of a step and the dominant kernel's launch duration: one extra solve with CUDA events
+    #      around every stage launch on the launching stream (the C library records them; torch events would only
+    #      see torch's stream)
+    import ctypes
+    stats = (ctypes.c_double * 6)()
+    lib.tg_set_stage_timing(1)
+    x.copy_(x0); flush.fill_(1)
+    tgb.solve(bt.spec, par, x, jacobian=args.jacobian, buffers=bufs, fused=args.fused)
+    torch.cuda.synchronize()
+    lib.tg_set_stage_timing(0)
+    lib.tg_last_solve_stats(stats, 6)
+    ms_ls, ms_qp, flops_qp, n_ls, n_qp, rounds = [float(v) for v in stats]
+    fp64_peak = ctypes.c_double(0.0)
+    _native.check(lib.tg_measure_fp64_peak(ctypes.byref(fp64_peak)), "tg_measure_fp64_peak")
+
     # ---- M1: evaluation kernel on the same batch
     xe = torch.from_numpy(synthetic.evaluation_points(bt)).to(dev)
     ev_out = {}
@@ -303,10 +322,6 @@ def main():
     # per-GPU figures for the rooflines (one launch = one batch on one GPU)
     solve_bytes = 8 * (L.P + 2 * L.n + 4) * B
     mean_nit = float(nit.mean())
-    # flops model of SURVEY.md 8(d): nit * [F_eval + n_ls F_val + (2 n^3/3 + 2 m n^2)]
-    f_eval = {"C2": 12.5e3, "C3": 22.5e3, "C4": 2.5e3}.get(name, 8.3e3)
-    flops_traj = mean_nit * (1.3 * f_eval + 2.0 * L.n ** 3 / 3 + 2.0 * L.m * L.n ** 2)
-    fp64_peak_tf = 148 * 64 * 2 * 1.965e9 / 1e12
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
@@ -315,14 +330,24 @@ def main():
                        "multi_gpu": "independent problems sharded by rank, one NCCL all-gather of result rows per step"},
             "solve_stats": {"mean_nit": mean_nit, "max_nit": int(nit.max()),
                             "status_histogram": {str(k): int(v) for k, v in zip(*np.unique(status, return_counts=True))}},
-            "roofline": {"kernel": "tg_solve_kernel", "bound": "hbm", "achieved": solve_bytes / (ms_step * 1e-3) / 1e9,
-                         "peak": hbm_peak, "unit": "GB/s", "frac": solve_bytes / (ms_step * 1e-3) / 1e9 / hbm_peak,
-                         "traffic": None, "peak_source": peak_src,
-                         "note": "the SQP kernel keeps each problem in shared memory; it is FP64/latency bound, see roofline_fp64"},
-            "roofline_fp64": {"kernel": "tg_solve_kernel", "model_flops_per_trajectory": flops_traj,
-                              "achieved": flops_traj * B / (ms_step * 1e-3) / 1e12, "peak": fp64_peak_tf, "unit": "TFLOP/s",
-                              "frac": flops_traj * B / (ms_step * 1e-3) / 1e12 / fp64_peak_tf,
-                              "peak_source": "148 SMs x 64 DFMA/clk x 2 x 1.965 GHz (nominal; not in MEASURED_PEAKS.json)"},
+            # dominant kernel of a step: the QP-stage kernel (share below).  It works out of shared memory; its bound is
+            # the FP64 pipe, so `achieved` is algorithmic fp64 operations (model count accumulated by the kernel per
+            # problem: 2 per multiply-add of the factor updates, products and scans it performs) / its launch time.
+            "roofline": ({"kernel": "tg_sqp_qp_kernel", "bound": "fp64", "achieved": flops_qp / (ms_qp * 1e-3) / 1e12,
+                          "peak": fp64_peak.value, "unit": "TFLOP/s", "frac": flops_qp / (ms_qp * 1e-3) / 1e12 / fp64_peak.value,
+                          "traffic": NCU_TRAFFIC.get(name),
+                          "launches_per_step": int(n_qp), "avg_launch_ms": ms_qp / max(n_qp, 1.0),
+                          "share_of_step": ms_qp / (ms_ls + ms_qp), "line_search_kernel_ms": ms_ls, "qp_kernel_ms": ms_qp,
+                          "algorithmic_flops_per_trajectory": flops_qp / B,
+                          "peak_source": "measured in this run: DFMA kernel, 8 chains per thread, every SM full "
+                                         "(MEASURED_PEAKS.json has no fp64 figure; nominal 148 x 64 x 2 x 1.965 GHz = 37.2)",
+                          "hbm": {"achieved": solve_bytes / (ms_step * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                                  "frac": solve_bytes / (ms_step * 1e-3) / 1e9 / hbm_peak, "peak_source": peak_src,
+                                  "note": "algorithmic HBM bytes per trajectory are 8(P + 2n + 4): not the bound"}}
+                         if not args.fused and ms_qp > 0 else
+                         {"kernel": "tg_solve_kernel", "bound": "hbm", "achieved": solve_bytes / (ms_step * 1e-3) / 1e9,
+                          "peak": hbm_peak, "unit": "GB/s", "frac": solve_bytes / (ms_step * 1e-3) / 1e9 / hbm_peak,
+                          "traffic": None, "peak_source": peak_src}),
             "evals": {"metric": "constraint_jacobian_evaluations_per_sec", "value": world * B / (ms_eval * 1e-3),
                       "unit": "evaluations/s", "ms_per_step": ms_eval, "bytes_per_eval": eval_bytes,
                       "e2e": {"value": eval_e2e, "unit": "evaluations/s", "h2d_bytes_per_step": h2d,
@@ -338,7 +363,7 @@ def main():
 
     # ---- CPU baseline on the box's host cores (rank 0, N = 1 only): bounded sample of the same problems
     if world == 1 and not args.no_cpu_baseline and cpu_path_available():
-        sample = args.cpu_sample or min(256, max(32, 2 * cores))
+        sample = args.cpu_sample or max(128, 16 * cores)
         try:
             dt, res, kind = run_cpu_sample(name, B, sample, cores)
             st_ref = np.array([r[1] for r in res]); x_ref = np.array([r[4] for r in res])

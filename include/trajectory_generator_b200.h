@@ -84,6 +84,16 @@ int tg_solve_host(const int *spec, int B, const double *par, double *x, double *
 /* number of kernel launches issued by this library since load (all entry points) */
 unsigned long long tg_launch_count(void);
 
+/* ---- measurement helpers (bench.py's roofline; not part of the reference's interface)
+ * tg_set_stage_timing(1): the following lock-step solves record CUDA events around every stage launch.
+ * tg_last_solve_stats: out[0..5] = {ms in line-search launches, ms in QP launches, model fp64 operation count of
+ *   the QP stage summed over the batch, line-search launches, QP launches, rounds} of the calling thread's last
+ *   solve with timing on; returns the number of values.
+ * tg_measure_fp64_peak: DFMA throughput of the current device in TFLOP/s (8 independent chains per thread). */
+void tg_set_stage_timing(int on);
+int tg_last_solve_stats(double *out, int cap);
+int tg_measure_fp64_peak(double *tflops);
+
 /* ------------------------------------------------------------------ (A) legacy symbols
  * Signatures of CC/include/CrossTermBounds.hpp:45-72, CC/include/ObstacleConstraints.hpp:25-49,
  * CC/include/DerivativeBounds.hpp:63-70 and CC/include/ControlPointDerivativeBounds.hpp:26-33

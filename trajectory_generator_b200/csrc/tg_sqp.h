@@ -37,6 +37,7 @@ struct TgSqpResult {
 // memory when the stages run as separate lock-step kernels); the SCRATCH part is only used inside a stage.
 struct TgSqpCtl {
     double f, f0, t0, h3, h4, alpha, acc;
+    double flops;        // algorithmic fp64 operations of the QP stage so far (model counts, see tg_sqp_stage_qp)
     int state, iter, ireset, line, badlin, nfev, status, need_reset, maxiter, flags;
 };
 enum { TG_ST_INIT = 0, TG_ST_QP, TG_ST_LS, TG_ST_UPDATE, TG_ST_DONE };
@@ -356,7 +357,7 @@ TG_QFN void tg_qp_drop(const TgSqpWs &W, int nq, int &iq, int l)
     TG_SYNC();
 }
 
-TG_QFN int tg_qp_solve(const TgSqpWs &W, int nq, int meq, double rho)
+TG_QFN int tg_qp_solve(const TgSqpWs &W, int nq, int meq, double rho, double &fl)
 {
     const int lane = TG_LANE(), n = W.n, ld = W.ldq, m = W.m;
     const int nc = m + 2 * W.n1;
@@ -401,6 +402,7 @@ TG_QFN int tg_qp_solve(const TgSqpWs &W, int nq, int meq, double rho)
     TG_SYNC();
     int iq = 0;
     double d2n, dn;
+    fl += (double)n * n * n / 3 + 4.0 * nq * nq;          // J = L^-T D^-1/2 ; xq = -J J'g
     // ---- the equality rows in order (outer steps 0 .. meq-1), then the most violated inequality row or bound
     const int itmax = 10 * (nc + nq) + 100;
     #pragma unroll 1
@@ -432,6 +434,7 @@ TG_QFN int tg_qp_solve(const TgSqpWs &W, int nq, int meq, double rho)
                 if (sv < -tol && sv < best) { best = sv; ip = p; }
             }
             tg_wargmin(best, ip);
+            fl += 3.0 * (m - meq) * nq;
             if (ip == 0x7fffffff) {
                 #pragma unroll 1
                 for (int k = lane; k < iq; k += TG_NL) W.r[W.act[k]] = W.uq[k];
@@ -445,6 +448,7 @@ TG_QFN int tg_qp_solve(const TgSqpWs &W, int nq, int meq, double rho)
         #pragma unroll 1
         for (int inner = 0; inner < itmax; inner++) {
             tg_qp_directions(W, nq, iq, d2n, dn);
+            fl += 2.0 * nq * nq + 2.0 * nq * (nq - iq) + (double)iq * iq + 4.0 * nq;
             // dual step length: active inequalities whose multiplier would turn negative
             double t1 = INFINITY; int l = 0x7fffffff;
             if (!eq) {
@@ -473,9 +477,11 @@ TG_QFN int tg_qp_solve(const TgSqpWs &W, int nq, int meq, double rho)
                 if (lane == 0) { W.uq[iq] = uip; W.act[iq] = ip; W.iact[ip] = 1; }
                 TG_SYNC();
                 tg_qp_add(W, nq, iq, d2n);
+                fl += 2.0 * nq * (nq - iq) + 3.0 * nq;
                 iq++;
                 break;
             }
+            fl += 6.0 * (iq - 1 - l) * (nq + 0.5 * (iq - 1 - l));
             tg_qp_drop(W, nq, iq, l);
             if (primal) {
                 sv = tg_qp_value(W, nq, ip);
@@ -573,7 +579,7 @@ TG_FN void tg_sqp_begin(const TgLayout &L, const TgSqpWs &W, const double *xin, 
     for (int q = lane; q < W.lda * n1; q += TG_NL) W.A[q] = 0;
     if (lane == 0) {
         TgSqpCtl c;
-        c.f = 0; c.f0 = 0; c.t0 = 0; c.h3 = 0; c.h4 = 1; c.alpha = 1; c.acc = acc;
+        c.f = 0; c.f0 = 0; c.t0 = 0; c.h3 = 0; c.h4 = 1; c.alpha = 1; c.acc = acc; c.flops = 0;
         c.state = TG_ST_INIT; c.iter = 0; c.ireset = 0; c.line = 0; c.badlin = 0; c.nfev = 0; c.status = -1;
         c.need_reset = 1; c.maxiter = maxiter; c.flags = flags;
         *W.ctl = c;
@@ -638,6 +644,7 @@ TG_QFN void tg_sqp_stage_qp(const TgLayout &L, const TgSqpWs &W)
     TgSqpCtl ctl = *W.ctl;
     const double acc = ctl.acc, tol = 10 * ctl.acc;
     double h1, h2, h3;
+    double fl = 0;       // model count of the stage's fp64 operations (2 per multiply-add), for the roofline report
     if (ctl.state == TG_ST_UPDATE) {
         // ---- convergence test after the step
         double sn = 0;
@@ -670,6 +677,7 @@ TG_QFN void tg_sqp_stage_qp(const TgLayout &L, const TgSqpWs &W)
                 for (int i = lane; i < n; i += TG_NL) W.u[i] = h4 * W.u[i] + (1 - h4) * W.v[i];
             }
             TG_SYNC();
+            fl += 2.0 * n * m + 6.0 * n * n + 8.0 * n;         // u = grad L - gl ; v = B s ; two rank-one updates of L D L'
             if (h1 == 0 || h2 == 0) ctl.need_reset = 1;
             else {
                 #pragma unroll 1
@@ -716,7 +724,7 @@ TG_QFN void tg_sqp_stage_qp(const TgLayout &L, const TgSqpWs &W)
             double rho = 0;
             #pragma unroll 1
             for (int attempt = 0; attempt < 7; attempt++) {
-                mode = tg_qp_solve(W, nq, meq, rho);
+                mode = tg_qp_solve(W, nq, meq, rho, fl);
                 if (attempt == 0) {
                     if (mode == 6 && n == meq) mode = 4;
                     if (mode != 4) break;
@@ -731,6 +739,13 @@ TG_QFN void tg_sqp_stage_qp(const TgLayout &L, const TgSqpWs &W)
                     rho *= 10;
                 }
             }
+#if defined(TG_QP_DEBUG) && !defined(__CUDA_ARCH__)
+            {
+                double dmin = 1e300, dmax = 0;
+                for (int i = 0; i < n; i++) { dmin = fmin(dmin, W.Dd[i]); dmax = fmax(dmax, W.Dd[i]); }
+                printf("iter %3d mode %d badlin %d rho %.0e  D in [%.2e, %.2e]  f %.8g\n", ctl.iter, mode, ctl.badlin, rho, dmin, dmax, ctl.f);
+            }
+#endif
             if (mode != TG_QP_OK) { ctl.status = mode; ctl.state = TG_ST_DONE; break; }
             if (ctl.badlin) ctl.h4 = 1 - W.xq[n];
             // ---- gradient of the Lagrangian at the old point, merit weights
@@ -744,6 +759,7 @@ TG_QFN void tg_sqp_stage_qp(const TgLayout &L, const TgSqpWs &W)
                 W.x0[i] = W.x[i];
             }
             ctl.f0 = ctl.f;
+            fl += 2.0 * n * m + 8.0 * m + 4.0 * n;
             TG_SYNC();
             double gs = 0;
             #pragma unroll 1
@@ -778,6 +794,7 @@ TG_QFN void tg_sqp_stage_qp(const TgLayout &L, const TgSqpWs &W)
             ctl.state = TG_ST_LS;
         } while (0);
     }
+    ctl.flops += fl;
     TG_SYNC();
     if (lane == 0) *W.ctl = ctl;
     TG_SYNC();
