@@ -41,7 +41,9 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="C2", help="C2 (default, BASELINE configs[1]) | C3 | C4 | C5a | C5c")
     ap.add_argument("--batch", type=int, default=None, help="problems per GPU (default: the config's full batch)")
-    ap.add_argument("--jacobian", default="analytic", choices=["analytic", "fd"])
+    ap.add_argument("--jacobian", default="fd", choices=["analytic", "fd"],
+                    help="fd (default): scipy's forward differences emulated on the GPU -- the mode whose converged control points "
+                         "match the reference within 1e-5; analytic: closed-form Jacobians (reported next to it as analytic_mode)")
     ap.add_argument("--cpu-sample", type=int, default=None, help="problems in the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--fused", action="store_true", help="one persistent solve kernel instead of lock-step stage kernels")
@@ -53,7 +55,8 @@ def parse():
 # the native steps run in the reference's own C++ compiled unmodified when oracle/_ref exists)
 # --------------------------------------------------------------------------------------------------------------
 def _cpu_worker(args):
-    name, seed_batch, indices, native_kind = args
+    name, seed_batch, indices, native_kind = args[:4]
+    perturb = len(args) > 4 and args[4]
     import warnings
     warnings.simplefilter("ignore")
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
@@ -65,6 +68,9 @@ def _cpu_worker(args):
         d, cc, kw = synthetic.container_for(batch, i)
         op = tg_oracle.OracleProblem(d, cc, kw.get("objective_function_type", synthetic.OBJECTIVE[name]),
                                      kw.get("num_intervals_free_space"), native_kind=native_kind)
+        if perturb:
+            # the same reference solve started one unit in the last place away from x0 (its own reproducibility)
+            op.x0 = np.nextafter(op.x0, np.inf)
         t = time.perf_counter()
         res = op.solve()
         out.append((i, int(res.status), int(res.nit), time.perf_counter() - t, res.x.tolist()))
@@ -77,7 +83,7 @@ def cpu_path_available():
     return "ref" if ref else ("oracle" if port else None)
 
 
-def run_cpu_sample(name, gen_batch, sample, procs):
+def run_cpu_sample(name, gen_batch, sample, procs, perturb=False):
     """Solves problems [0, sample) of the synthetic batch with a process pool.  Returns (seconds, results)."""
     import multiprocessing as mp
     kind = cpu_path_available()
@@ -89,7 +95,7 @@ def run_cpu_sample(name, gen_batch, sample, procs):
     with ctx.Pool(len(chunks)) as pool:
         pool.map(_noop, range(len(chunks)))            # start the workers before the clock
         t = time.perf_counter()
-        parts = pool.map(_cpu_worker, [(name, gen_batch, c, kind) for c in chunks])
+        parts = pool.map(_cpu_worker, [(name, gen_batch, c, kind, perturb) for c in chunks])
         dt = time.perf_counter() - t
     res = sorted(r for p in parts for r in p)
     return dt, res, kind
@@ -265,6 +271,19 @@ def main():
     fp64_peak = ctypes.c_double(0.0)
     _native.check(lib.tg_measure_fp64_peak(ctypes.byref(fp64_peak)), "tg_measure_fp64_peak")
 
+    # ---- the other Jacobian mode on the same batch (2 timed steps), reported next to the headline
+    other = "analytic" if args.jacobian == "fd" else "fd"
+    def other_step():
+        tgb.solve(bt.spec, par, x, jacobian=other, buffers=bufs, fused=args.fused)
+    barrier()
+    ms_o = timed(other_step, 2, 1, prepare=lambda: x.copy_(x0))
+    barrier()
+    toto = torch.tensor([sum(ms_o)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(toto, op=dist.ReduceOp.MAX)
+    other_ms = toto.item() / 2
+    other_status = bufs.status.cpu().numpy(); other_nit = bufs.nit.cpu().numpy(); other_x = x.cpu().numpy()
+
     # ---- M1: evaluation kernel on the same batch
     xe = torch.from_numpy(synthetic.evaluation_points(bt)).to(dev)
     ev_out = {}
@@ -358,6 +377,9 @@ def main():
                                    "peak_source": peak_src}},
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "api": "tg_solve_host (C-ABI, host buffers; copies inside the call)"},
+            other + "_mode": {"value": world * B / (other_ms * 1e-3), "unit": UNIT, "ms_per_step": other_ms, "steps": 2,
+                              "mean_nit": float(other_nit.mean()),
+                              "status_histogram": {str(k): int(v) for k, v in zip(*np.unique(other_status, return_counts=True))}},
             "gpu_launches": int(solve_launches),
             "clocks": sampler.summary()}
 
@@ -373,17 +395,31 @@ def main():
                                     "sample": "first %d problems of the same batch, scipy SLSQP with 2-point finite differences, process pool of %d" % (sample, cores),
                                     "seconds": dt,
                                     "status_histogram": {str(a): int(b) for a, b in zip(*np.unique(st_ref, return_counts=True))}}
+            # how reproducible the reference is against ITSELF: the same scipy solves started from x0 + 1 ulp.  Its
+            # forward differences (h = 1.5e-8) amplify last-place differences of the closures by 1/h, so that long
+            # solves separate; agreement of the CUDA path is therefore also reported on the subset of problems whose
+            # reference solution is stable to 1e-5 under that perturbation.
+            _, res2, _ = run_cpu_sample(name, B, sample, cores, perturb=True)
+            st2 = np.array([r[1] for r in res2]); x2 = np.array([r[4] for r in res2])
+            stable = (st_ref == 0) & (st2 == 0) & (np.abs(x2[:, :k] - x_ref[:, :k]).max(1) <= 1e-5)
             def agreement(xg, sg, mode):
                 dcp = np.abs(xg[:, :k] - x_ref[:, :k]).max(1)
                 both = (st_ref == 0) & (sg == 0)
                 return {"jacobian": mode, "problems": int(sample), "reference_status0": int((st_ref == 0).sum()),
                         "both_status0": int(both.sum()), "same_success_flag": int(((st_ref == 0) == (sg == 0)).sum()),
+                        "same_status": int((st_ref == sg).sum()),
                         "status0_within_1e-5": int((dcp[both] <= 1e-5).sum()),
-                        "status0_within_1e-3": int((dcp[both] <= 1e-3).sum())}
-            # the timed mode, and the finite-difference emulation that follows the reference's own iterates
-            fd = tgb.solve_host(bt.spec, bt.par[:sample], bt.x0[:sample], jacobian="fd")
+                        "status0_within_1e-3": int((dcp[both] <= 1e-3).sum()),
+                        "reference_stable_problems": int(stable.sum()),
+                        "reference_stable_within_1e-5": int((dcp[stable & (sg == 0)] <= 1e-5).sum())}
+            # the timed mode (first) and the other one
             line["parity_sample"] = [agreement(x_gpu[:sample], status[:sample], args.jacobian),
-                                     agreement(fd["x"], fd["status"], "fd")]
+                                     agreement(other_x[:sample], other_status[:sample], other)]
+            line["reference_self_consistency"] = {
+                "perturbation": "x0 + 1 ulp", "problems": int(sample), "both_status0": int(((st_ref == 0) & (st2 == 0)).sum()),
+                "same_status": int((st_ref == st2).sum()),
+                "status0_within_1e-5": int(stable.sum()),
+                "status0_within_1e-3": int(((st_ref == 0) & (st2 == 0) & (np.abs(x2[:, :k] - x_ref[:, :k]).max(1) <= 1e-3)).sum())}
         except Exception as exc:      # the baseline is reported, never required
             line["cpu_baseline"] = {"error": repr(exc)}
     print(json.dumps(line))

@@ -91,3 +91,37 @@ def test_fused_and_lockstep_kernels_agree(native_lib):
         assert ok.mean() > 0.6
         assert np.abs(a["x"][ok] - f["x"][ok]).max() <= 1e-5
         assert (a["status"] == 0).mean() > 0.7
+
+
+@pytest.mark.parametrize("name", ["obstacle2d", "sfc3d", "sfc3d_four"])
+def test_dropin_generate_trajectory_matches_reference(native_lib, name):
+    """The reference's public call, through the alias package: TrajectoryGenerator(d).generate_trajectory(container, ...)
+    returns the reference's (control_points[d,N], scale_factor, is_violation) within 1e-5 (fixtures recorded by running
+    the unmodified reference, TG/trajectory_generator.py:65-97)."""
+    from trajectory_generation.trajectory_generator import TrajectoryGenerator
+    d, cc, kw = problems.ALL[name](helpers.product_namespace())
+    s = helpers.load_golden()["problems"][name]["solve"]
+    gen = TrajectoryGenerator(d)
+    cps, scale, viol = gen.generate_trajectory(cc, **kw)
+    ref = np.array(s["control_points"], dtype=float)
+    assert cps.shape == ref.shape and cps.dtype == np.float64
+    assert np.abs(cps - ref).max() <= 1e-5
+    assert abs(scale - s["scale_factor"]) <= 1e-5
+    assert bool(viol) == bool(s["is_violation"])
+    assert gen.last_result.status == s["status"] == 0
+
+
+def test_generate_trajectories_groups_mixed_shapes(native_lib):
+    """Batched addition: containers of different shapes (2-D obstacles, 3-D corridors) in one call come back in input
+    order and equal the one-at-a-time answers."""
+    from trajectory_generator_b200.trajectory_generator import TrajectoryGenerator
+    ns = helpers.product_namespace()
+    items = [problems.ALL[n](ns) for n in ("sfc3d", "sfc3d_four", "sfc3d")]
+    gen = TrajectoryGenerator(3)
+    kw = items[0][2]
+    many = gen.generate_trajectories([it[1] for it in items], **kw)
+    assert len(many) == 3
+    for it, res in zip(items, many):
+        one = gen.generate_trajectory(it[1], **it[2])
+        assert res.control_points.shape == one[0].shape
+        assert np.array_equal(res.control_points, one[0]) and res.scale_factor == one[1]
