@@ -11,7 +11,7 @@ bufs = tgb.SolveBuffers(bt.spec, B, dev)
 for r in range(reps):
     x = x0.clone()
     s = torch.cuda.Event(enable_timing=True); e = torch.cuda.Event(enable_timing=True)
-    s.record(); out = tgb.solve(bt.spec, par, x, buffers=bufs); e.record(); torch.cuda.synchronize()
+    s.record(); out = tgb.solve(bt.spec, par, x, buffers=bufs, jacobian=(sys.argv[4] if len(sys.argv) > 4 else "fd")); e.record(); torch.cuda.synchronize()
     print("solve %d: %.1f ms, status0 %.3f mean nit %.1f" % (r, s.elapsed_time(e), (out["status"] == 0).float().mean().item(), out["nit"].float().mean().item()))
 xe = torch.from_numpy(syn.evaluation_points(bt)).to(dev)
 o = tgb.evaluate(bt.spec, par, xe); torch.cuda.synchronize()

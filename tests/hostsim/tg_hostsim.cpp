@@ -50,3 +50,34 @@ extern "C" int hs_solve(const int *spec, const double *par, double *x, int maxit
     return res.status;
 }
 #endif
+
+#ifdef TG_WITH_SQP
+// the solver's finite-difference derivatives at x (scipy's approx_derivative emulation): g[n], J[m*n] row-major
+// (linear rows hold their constant coefficients)
+extern "C" void hs_fd_derivatives(const int *spec, const double *par, const double *x, const double *xl, const double *xu,
+                                  double *g, double *J)
+{
+    TgLayout L;
+    tg_make_layout(spec, &L);
+    std::vector<double> ws(tg_sqp_workspace_doubles(L));
+    TgSqpWs W;
+    tg_sqp_carve(L, ws.data(), &W);
+    tg_sqp_begin(L, W, x, 100, 1e-6, TG_SQP_FD_JACOBIAN);
+    for (int i = 0; i < L.n; i++) { W.xl[i] = xl[i]; W.xu[i] = xu[i]; }
+    TgJac sink = {W.A, 1, W.lda, 0};
+    double f;
+    if (L.d == 2) {
+        tg_linear_jacobian_d<2>(L, spec, par, sink);
+        f = tg_sqp_evaluate<2>(L, spec, par, W, false);
+        tg_sqp_fd_derivatives<2>(L, spec, par, W, f);
+    } else {
+        tg_linear_jacobian_d<3>(L, spec, par, sink);
+        f = tg_sqp_evaluate<3>(L, spec, par, W, false);
+        tg_sqp_fd_derivatives<3>(L, spec, par, W, f);
+    }
+    for (int i = 0; i < L.n; i++) {
+        g[i] = W.g[i];
+        for (int j = 0; j < L.m; j++) J[j * L.n + i] = W.A[i * W.lda + j];
+    }
+}
+#endif

@@ -22,6 +22,16 @@ class HostSim:
         lib.hs_solve.argtypes = [NI, ND, ND, ctypes.c_int, ctypes.c_double, ctypes.c_int, ND, NI, NI, NI,
                                  ctypes.c_void_p, ctypes.c_int]
 
+    def fd_derivatives(self, pp, x):
+        """g[n], J[m, n] as the solver's finite-difference mode forms them at x"""
+        L = pp.layout
+        g = np.zeros(L.n); J = np.zeros((L.m, L.n))
+        self.lib.hs_fd_derivatives.argtypes = [NI, ND, ND, ND, ND, ND, ND]
+        xl = np.where(np.isfinite(pp.xl), pp.xl, -np.inf); xu = np.where(np.isfinite(pp.xu), pp.xu, np.inf)
+        self.lib.hs_fd_derivatives(pp.spec, pp.par, np.ascontiguousarray(x, dtype=np.float64),
+                                   np.ascontiguousarray(xl), np.ascontiguousarray(xu), g, J)
+        return g, J
+
     def eval(self, pp, x, jac=True):
         L = pp.layout
         f = np.zeros(1); g = np.zeros(L.n); c = np.zeros(L.m); J = np.zeros((L.m, L.n))

@@ -37,6 +37,21 @@
 #else
 #define TG_FN static inline
 #endif
+// the cubic solver (two call sites per interval evaluation) stays out of line in the solver's kernels: one copy
+// keeps the code of a finite-difference sweep within reach of the instruction cache
+#if defined(__CUDACC__) && !defined(TG_INLINE_LEAVES)
+#define TG_LEAF static __host__ __device__ __noinline__
+#else
+#define TG_LEAF TG_FN
+#endif
+
+// translation units that call the whole-problem evaluators from several places (the solver's line-search stage:
+// evaluation, finite-difference sweep) define TG_SHARED_EVALUATORS: one out-of-line copy instead of one per call site
+#if defined(__CUDACC__) && defined(TG_SHARED_EVALUATORS)
+#define TG_EVAL_FN static __host__ __device__ __noinline__
+#else
+#define TG_EVAL_FN TG_FN
+#endif
 
 // A problem is evaluated by a GROUP of TG_GS consecutive lanes of a warp (TG_GS = 8, 16 or 32, fixed per
 // translation unit): with 5..14 intervals per spline a full warp leaves most lanes idle in the per-interval
@@ -195,7 +210,7 @@ TG_HD double *tg_jrow(const TgJac &J, const TgLayout &L, int r)
 // ---------------------------------------------------------------------------
 // cubic solver, CC/src/CubicEquationSolver.cpp:8-117 (absent roots = DBL_MAX)
 // ---------------------------------------------------------------------------
-TG_FN void tg_solve_cubic_eq(double a, double b, double c, double d, double r[3])
+TG_LEAF void tg_solve_cubic_eq(double a, double b, double c, double d, double r[3])
 {
     r[0] = r[1] = r[2] = DBL_MAX;
     if (a == 0) {
@@ -255,12 +270,14 @@ struct TgInterval {
 
 // control points of interval j out of the row-major d x N block of x
 // (CC/src/CBindHelperFunctions.cpp:11-31); `first` trims the window.
+// (pi, pv): entry pi of x is read as pv -- a finite-difference perturbation applied on load.
+#define TG_XP(idx) ((idx) == pi ? pv : x[idx])
 template <int D>
-TG_HD void tg_load_interval(const double *x, int N, int j, TgInterval<D> &I)
+TG_HD void tg_load_interval(const double *x, int N, int j, TgInterval<D> &I, int pi = -1, double pv = 0)
 {
 #pragma unroll
     for (int c = 0; c < D; c++) {
-        const double p0 = x[c * N + j], p1 = x[c * N + j + 1], p2 = x[c * N + j + 2], p3 = x[c * N + j + 3];
+        const double p0 = TG_XP(c * N + j), p1 = TG_XP(c * N + j + 1), p2 = TG_XP(c * N + j + 2), p3 = TG_XP(c * N + j + 3);
         I.k3[c] = p0 * (-1 / 6.0) + p1 * (1 / 2.0) + p2 * (-1 / 2.0) + p3 * (1 / 6.0);
         I.k2[c] = p0 * (1 / 2.0) + p1 * (-1.0) + p2 * (1 / 2.0);
         I.k1[c] = p0 * (-1 / 2.0) + p2 * (1 / 2.0);
@@ -506,12 +523,13 @@ TG_HD double tg_minvo_py(int l, int k)
 // CC/src/SphereCollisionEvaluator.cpp:88-154 (rotation written as the unit
 // vector u = first row of R).  gl (optional): d dist / d P. ----
 template <int D>
-TG_FN double tg_hull_distance(const double *x, int N, int j, const double *center, double radius, double *gl)
+TG_FN double tg_hull_distance(const double *x, int N, int j, const double *center, double radius, double *gl,
+                              int pi = -1, double pv = 0)
 {
     double q[D][4], w[D];
 #pragma unroll
     for (int c = 0; c < D; c++) {
-        const double p0 = x[c * N + j], p1 = x[c * N + j + 1], p2 = x[c * N + j + 2], p3 = x[c * N + j + 3];
+        const double p0 = TG_XP(c * N + j), p1 = TG_XP(c * N + j + 1), p2 = TG_XP(c * N + j + 2), p3 = TG_XP(c * N + j + 3);
 #pragma unroll
         for (int k = 0; k < 4; k++)
             q[c][k] = p0 * tg_minvo(0, k) + p1 * tg_minvo(1, k) + p2 * tg_minvo(2, k) + p3 * tg_minvo(3, k);
@@ -573,7 +591,7 @@ TG_HD double tg_diff(const double *row, int k, int j)
 }
 
 // returns f on every lane; g (n entries, optional) is complete after TG_SYNC()
-TG_FN double tg_objective(const TgLayout &L, const int *sp, const double *x, double *g)
+TG_EVAL_FN double tg_objective(const TgLayout &L, const int *sp, const double *x, double *g)
 {
     const int obj = sp[TG_SP_OBJECTIVE], d = L.d, N = L.N, lane = TG_LANE();
     const double al = x[L.ia];
@@ -1130,7 +1148,9 @@ TG_FN void tg_rows_obstacles(const TgLayout &L, const int *sp, const double *par
     TG_SYNC();
 }
 
-TG_HD int tg_scratch_doubles(const TgLayout &L) { return L.n_obs * L.nint > 0 ? L.n_obs * L.nint : 1; }
+// per-problem scratch of the evaluators: obstacle x interval distances, and for the item-parallel finite-difference
+// sweeps (tg_fd_turning / tg_fd_obstacles) 4 perturbed values per control-point variable + 2 per interval
+TG_HD int tg_scratch_doubles(const TgLayout &L) { return (L.n_obs * L.nint > 0 ? L.n_obs * L.nint : 1) + 4 * L.d * L.N + 2 * L.nint + 2; }
 
 // zero every nonlinear Jacobian row (they are rewritten sparsely on each evaluation)
 TG_FN void tg_zero_nonlinear_rows(const TgLayout &L, const TgJac &J)
@@ -1146,21 +1166,155 @@ TG_FN void tg_zero_nonlinear_rows(const TgLayout &L, const TgJac &J)
     TG_SYNC();
 }
 
-// all constraint values (m) and, if J, the nonlinear Jacobian rows
+// all constraint values (m) and, if J, the nonlinear Jacobian rows.  skip: blocks to leave untouched -- the solver's
+// finite-difference sweeps need neither the linear rows (terminal locations, corridors) nor the blocks that have
+// their own item-parallel sweep.
+#define TG_SKIP_LINEAR 1
+#define TG_SKIP_TURNING 2
+#define TG_SKIP_OBSTACLES 4
 template <int D>
-TG_FN void tg_constraints_d(const TgLayout &L, const int *sp, const double *par, const double *x, double *cv,
-                            const TgJac *J, double *scratch)
+TG_EVAL_FN void tg_constraints_d(const TgLayout &L, const int *sp, const double *par, const double *x, double *cv,
+                            const TgJac *J, double *scratch, int skip = 0)
 {
+    const bool nl_only = (skip & TG_SKIP_LINEAR) != 0;
     if (J) tg_zero_nonlinear_rows(L, *J);
-    tg_rows_location(L, sp, par, x, cv);
+    if (!nl_only) tg_rows_location(L, sp, par, x, cv);
     if (L.n_sder + L.n_eder) tg_rows_terminal(L, sp, par, x, cv, J);
     if (L.niw) tg_rows_intermediate(L, sp, par, x, cv, J);
     if (L.n_db) tg_rows_derivative<D>(L, sp, par, x, cv, J);
     if (L.n_tan) tg_rows_tangential<D>(L, sp, par, x, cv, J);
-    if (L.n_turn) tg_rows_turning<D>(L, sp, par, x, cv, J);
-    if (L.n_sfc) tg_rows_sfc<D>(L, sp, par, x, cv);
-    if (L.n_obs) tg_rows_obstacles<D>(L, sp, par, x, cv, J, scratch);
+    if (L.n_turn && !(skip & TG_SKIP_TURNING)) tg_rows_turning<D>(L, sp, par, x, cv, J);
+    if (L.n_sfc && !nl_only) tg_rows_sfc<D>(L, sp, par, x, cv);
+    if (L.n_obs && !(skip & TG_SKIP_OBSTACLES)) tg_rows_obstacles<D>(L, sp, par, x, cv, J, scratch);
     TG_SYNC();
+}
+
+// ---------------------------------------------------------------------------
+// Item-parallel forward differences of the two heavy blocks, as scipy forms them for the reference
+// (approx_derivative '2-point', abs_step = TG_FD_STEP, bounds):  A[i * lda + row] = (c(x + h_i e_i) - c(x)) / dx_i.
+// A control-point variable only moves the (at most 4) intervals that contain it, so instead of n full
+// re-evaluations the lanes work through the (interval, local control point, coordinate) items -- each one interval
+// evaluation with the perturbation applied on load -- and the max / min over intervals is then taken per variable
+// over perturbed values inside its window and base values outside.  Same numbers as n full evaluations.
+// ---------------------------------------------------------------------------
+#define TG_FD_STEP 1.4901161193847656e-08     // scipy/optimize/_slsqp_py.py:34
+
+// bound-aware forward step (scipy/optimize/_numdiff.py: the step is flipped when x + h leaves [lo, hi] and the
+// other side has room)
+TG_HD double tg_fd_step(double xi, double lo, double hi)
+{
+    double h = TG_FD_STEP;
+    const double xt = xi + h;
+    if (xt < lo || xt > hi) {
+        const double ld = xi - lo, ud = hi - xi;
+        if (fabs(h) <= fmax(ld, ud)) h = -h;
+        else h = ud >= ld ? ud : -ld;
+    }
+    return h;
+}
+
+// scr: 4 d N + 2 nint doubles
+template <int D>
+TG_EVAL_FN void tg_fd_turning(const TgLayout &L, const int *sp, const double *par, const double *x, const double *xl,
+                         const double *xu, double c0, double *A, int lda, double *scr)
+{
+    const int N = L.N, lane = TG_LANE(), kind = sp[TG_SP_TURN], n = L.n;
+    const int first = L.turn_first, ncp = L.turn_ncp, nint = ncp - 3, row = L.r_turn;
+    const double al = x[L.ia];
+    const double scale = kind == TG_TURN_CURVATURE ? 100.0 : 1.0;
+    double *base = scr, *pa = scr + nint, *pert = scr + 2 * nint;
+    const double ha = tg_fd_step(al, xl[L.ia], xu[L.ia]);
+    // base and alpha-perturbed bound of every interval; then one item per (interval, coordinate, local control point)
+    #pragma unroll 1
+    for (int q = lane; q < 2 * nint + nint * 4 * D; q += TG_NL) {
+        TgInterval<D> I;
+        int j, pi = -1;
+        double pv = 0, *dst;
+        if (q < 2 * nint) {
+            j = q < nint ? q : q - nint;
+            dst = q < nint ? base + j : pa + j;
+        } else {
+            const int r = q - 2 * nint;
+            j = r / (4 * D);
+            const int cl = r - j * 4 * D, c = cl >> 2, l = cl & 3;
+            pi = c * N + first + j + l;
+            pv = x[pi] + tg_fd_step(x[pi], xl[pi], xu[pi]);
+            dst = pert + (c * ncp + j + l) * 4 + l;
+        }
+        tg_load_interval<D>(x, N, first + j, I, pi, pv);
+        *dst = tg_interval_turn_bound<D>(I, (q >= nint && q < 2 * nint) ? al + ha : al, kind, 0);
+    }
+    TG_SYNC();
+    #pragma unroll 1
+    for (int i = lane; i < n; i += TG_NL) {
+        const int c = i / N, p = i - c * N - first;
+        double entry = 0;
+        if ((i < D * N && p >= 0 && p < ncp) || i == L.ia) {
+            double best = 0;
+            #pragma unroll 1
+            for (int j = 0; j < nint; j++) {
+                const int l = p - j;
+                const double b = i == L.ia ? pa[j] : ((l >= 0 && l <= 3) ? pert[(c * ncp + p) * 4 + l] : base[j]);
+                if (b > best) best = b;
+            }
+            const double cp = -((best - par[L.p_turn]) * scale);
+            const double dx = (x[i] + tg_fd_step(x[i], xl[i], xu[i])) - x[i];
+            entry = (cp - c0) / dx;
+        }
+        A[i * lda + row] = entry;
+    }
+    TG_SYNC();
+}
+
+// scr: K nint + 4 d N doubles (the first K nint are the base distances, as tg_rows_obstacles leaves them)
+template <int D>
+TG_EVAL_FN void tg_fd_obstacles(const TgLayout &L, const double *par, const double *x, const double *xl, const double *xu,
+                           const double *cbase, double *A, int lda, double *scr)
+{
+    const int N = L.N, nint = L.nint, K = L.n_obs, lane = TG_LANE(), n = L.n;
+    double *base = scr, *pert = scr + K * nint;
+    #pragma unroll 1
+    for (int q = lane; q < K * nint; q += TG_NL) {
+        const int k = q / nint, j = q - k * nint;
+        double ctr[D];
+#pragma unroll
+        for (int c = 0; c < D; c++) ctr[c] = par[L.p_obs_c + c * K + k];
+        base[q] = tg_hull_distance<D>(x, N, j, ctr, par[L.p_obs_r + k], 0);
+    }
+    TG_SYNC();
+    #pragma unroll 1
+    for (int k = 0; k < K; k++) {
+        double ctr[D];
+#pragma unroll
+        for (int c = 0; c < D; c++) ctr[c] = par[L.p_obs_c + c * K + k];
+        const double rad = par[L.p_obs_r + k];
+        #pragma unroll 1
+        for (int r = lane; r < nint * 4 * D; r += TG_NL) {
+            const int j = r / (4 * D), cl = r - j * 4 * D, c = cl >> 2, l = cl & 3;
+            const int i = c * N + j + l;
+            const double pv = x[i] + tg_fd_step(x[i], xl[i], xu[i]);
+            pert[i * 4 + l] = tg_hull_distance<D>(x, N, j, ctr, rad, 0, i, pv);
+        }
+        TG_SYNC();
+        #pragma unroll 1
+        for (int i = lane; i < n; i += TG_NL) {
+            double entry = 0;
+            if (i < D * N) {
+                const int p = i % N;
+                double best = DBL_MAX;
+                #pragma unroll 1
+                for (int j = 0; j < nint; j++) {
+                    const int l = p - j;
+                    const double v = (l >= 0 && l <= 3) ? pert[i * 4 + l] : base[k * nint + j];
+                    if (best > v) best = v;
+                }
+                const double dx = (x[i] + tg_fd_step(x[i], xl[i], xu[i])) - x[i];
+                entry = (best - cbase[L.r_obs + k]) / dx;
+            }
+            A[i * lda + L.r_obs + k] = entry;
+        }
+        TG_SYNC();
+    }
 }
 
 // constant Jacobian rows of the linear blocks (full-row sink only: compact == 0)

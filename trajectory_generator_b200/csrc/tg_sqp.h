@@ -55,6 +55,14 @@ struct TgSqpWs {
 
 TG_HD int tg_odd(int v) { return v | 1; }
 
+// unroll factor of the sequential inner products / updates of the QP stage (trip counts are n <= 62)
+#ifndef TG_UNROLL_N
+#define TG_UNROLL_N 4
+#endif
+#define TG_PRAGMA_(x) _Pragma(#x)
+#define TG_PRAGMA(x) TG_PRAGMA_(x)
+#define TG_UNROLL_INNER TG_PRAGMA(unroll TG_UNROLL_N)
+
 // The QP-stage functions are inlined into the lock-step QP kernel (one call site each; with the workspace carved
 // from the kernel's shared array the compiler then knows the address space of every access).  The fused kernel's
 // translation unit defines TG_SQP_NOINLINE (instruction-cache footprint).
@@ -66,9 +74,12 @@ TG_HD int tg_odd(int v) { return v | 1; }
 
 // Carves the per-problem state.  The persistent block is [ctl | x xl xu g s x0 | c mu | gl r Lm Dd | A]; its first
 // `npre` doubles (everything the line-search stage touches except A) may be staged at `prefix` while the rest
-// stays at `pbase` (+ offset) -- pass prefix == pbase for one contiguous block.  Sizes come back in doubles.
-TG_HD void tg_sqp_carve3(const TgLayout &L, double *prefix, double *pbase, double *sbase, TgSqpWs *W, size_t *np_,
-                         size_t *ns_, size_t *npre_)
+// stays at `pbase` (+ offset) -- pass prefix == pbase for one contiguous block.  The scratch block is
+// [QP-stage scratch | evaluation scratch (cf, evaluators' scratch)]; `ebase` != 0 places the evaluation scratch
+// elsewhere (the line-search kernel only allocates that part, the QP kernel only the first: *nsq_ doubles).
+// Sizes come back in doubles.
+TG_HD void tg_sqp_carve4(const TgLayout &L, double *prefix, double *pbase, double *sbase, double *ebase, TgSqpWs *W,
+                         size_t *np_, size_t *ns_, size_t *npre_, size_t *nsq_)
 {
     const int n = L.n, n1 = n + 1, m = L.m;
     TgSqpWs w;
@@ -86,16 +97,24 @@ TG_HD void tg_sqp_carve3(const TgLayout &L, double *prefix, double *pbase, doubl
     TG_TAKE(A, w.lda * n1);
     if (np_) *np_ = o;
     o = 0; base = sbase;
-    TG_TAKE(cf, m + 1); TG_TAKE(scratch, tg_scratch_doubles(L));       // <- all the line-search stage needs
     TG_TAKE(u, n1); TG_TAKE(v, n1); TG_TAKE(w, n1);
     TG_TAKE(Jq, w.ldq * n1); TG_TAKE(R, w.ldq * n1);
     TG_TAKE(z, n1); TG_TAKE(dq, n1); TG_TAKE(rq, n1); TG_TAKE(np, n1); TG_TAKE(uq, n1 + 1); TG_TAKE(xq, n1); TG_TAKE(hw, n1);
     TG_TAKE(rdi, n1);
     double *ints = base + o; o += (size_t)((n1 + 1 + w.nc + 1) / 2 + 1);
     w.act = (int *)ints; w.iact = w.act + n1 + 1;
+    if (nsq_) *nsq_ = o;
+    if (ebase) { base = ebase - o; }
+    TG_TAKE(cf, m + 1); TG_TAKE(scratch, tg_scratch_doubles(L));       // <- all the line-search stage needs
 #undef TG_TAKE
     if (ns_) *ns_ = o;
     if (W) *W = w;
+}
+
+TG_HD void tg_sqp_carve3(const TgLayout &L, double *prefix, double *pbase, double *sbase, TgSqpWs *W, size_t *np_,
+                         size_t *ns_, size_t *npre_)
+{
+    tg_sqp_carve4(L, prefix, pbase, sbase, 0, W, np_, ns_, npre_, 0);
 }
 
 TG_HD void tg_sqp_carve2(const TgLayout &L, double *pbase, double *sbase, TgSqpWs *W, size_t *np_, size_t *ns_)
@@ -103,9 +122,9 @@ TG_HD void tg_sqp_carve2(const TgLayout &L, double *pbase, double *sbase, TgSqpW
     tg_sqp_carve3(L, pbase, pbase, sbase, W, np_, ns_, 0);
 }
 
-// scratch needed by the line-search stage alone: cf + the obstacle scratch (carved like the full scratch so that
-// the same TgSqpWs works; u..hw are unused there and left dangling inside the small block)
+// scratch needed by the line-search stage alone (cf + the evaluators' scratch) / by the QP stage alone
 TG_HD size_t tg_sqp_ls_scratch_doubles(const TgLayout &L) { return (size_t)L.m + 1 + tg_scratch_doubles(L); }
+TG_HD size_t tg_sqp_qp_scratch_doubles(const TgLayout &L) { size_t a, b, c, d; tg_sqp_carve4(L, 0, 0, 0, 0, 0, &a, &b, &c, &d); return d; }
 TG_HD size_t tg_sqp_prefix_doubles(const TgLayout &L) { size_t a, b, c; tg_sqp_carve3(L, 0, 0, 0, 0, &a, &b, &c); return c; }
 
 TG_HD size_t tg_sqp_persistent_doubles(const TgLayout &L) { size_t a, b; tg_sqp_carve2(L, 0, 0, 0, &a, &b); return a; }
@@ -196,7 +215,7 @@ TG_QFN void tg_ldl_apply(int n, const double *Lm, const double *Dd, const double
     #pragma unroll 1
     for (int i = lane; i < n; i += TG_NL) {
         double h = s[i];
-        #pragma unroll 4
+        TG_UNROLL_INNER
         for (int j = i + 1; j < n; j++) h += Lm[i * n + j] * s[j];
         tmp[i] = Dd[i] * h;
     }
@@ -204,7 +223,7 @@ TG_QFN void tg_ldl_apply(int n, const double *Lm, const double *Dd, const double
     #pragma unroll 1
     for (int i = lane; i < n; i += TG_NL) {
         double h = tmp[i];
-        #pragma unroll 4
+        TG_UNROLL_INNER
         for (int j = 0; j < i; j++) h += Lm[j * n + i] * tmp[j];
         out[i] = h;
     }
@@ -259,7 +278,7 @@ TG_QFN void tg_qp_directions(const TgSqpWs &W, int nq, int iq, double &d2n, doub
     for (int k = lane; k < nq; k += TG_NL) {
         double h = 0;
         const double *col = W.Jq + k * ld;
-        #pragma unroll 4
+        TG_UNROLL_INNER
         for (int i = 0; i < nq; i++) h += col[i] * W.np[i];
         W.dq[k] = h;
         W.hw[k] = h;
@@ -272,7 +291,7 @@ TG_QFN void tg_qp_directions(const TgSqpWs &W, int nq, int iq, double &d2n, doub
     #pragma unroll 1
     for (int i = lane; i < nq; i += TG_NL) {
         double h = 0;
-        #pragma unroll 4
+        TG_UNROLL_INNER
         for (int k = iq; k < nq; k++) h += W.Jq[k * ld + i] * W.dq[k];
         W.z[i] = h;
     }
@@ -305,7 +324,7 @@ TG_QFN void tg_qp_add(const TgSqpWs &W, int nq, int iq, double d2n)
         for (int i = lane; i < nq; i += TG_NL) {
             const double t = (W.z[i] - sigma * W.Jq[iq * ld + i]) * sc;
             W.Jq[iq * ld + i] -= t * w0;
-            #pragma unroll 4
+            TG_UNROLL_INNER
             for (int k = iq + 1; k < nq; k++) W.Jq[k * ld + i] -= t * W.dq[k];
         }
     }
@@ -372,7 +391,7 @@ TG_QFN int tg_qp_solve(const TgSqpWs &W, int nq, int meq, double rho, double &fl
             #pragma unroll 1
             for (int i = k - 1; i >= 0; i--) {
                 double h = 0;
-                #pragma unroll 4
+                TG_UNROLL_INNER
                 for (int j = i + 1; j <= k; j++) h += W.Lm[i * n + j] * col[j];
                 col[i] = -h;
             }
@@ -387,7 +406,7 @@ TG_QFN int tg_qp_solve(const TgSqpWs &W, int nq, int meq, double rho, double &fl
     #pragma unroll 1
     for (int k = lane; k < nq; k += TG_NL) {
         double h = 0;
-        #pragma unroll 4
+        TG_UNROLL_INNER
         for (int i = 0; i < nq; i++) h += W.Jq[k * ld + i] * W.g[i];
         W.dq[k] = h;
     }
@@ -395,7 +414,7 @@ TG_QFN int tg_qp_solve(const TgSqpWs &W, int nq, int meq, double rho, double &fl
     #pragma unroll 1
     for (int i = lane; i < nq; i += TG_NL) {
         double h = 0;
-        #pragma unroll 4
+        TG_UNROLL_INNER
         for (int k = 0; k < nq; k++) h += W.Jq[k * ld + i] * W.dq[k];
         W.xq[i] = -h;
     }
@@ -418,7 +437,7 @@ TG_QFN int tg_qp_solve(const TgSqpWs &W, int nq, int meq, double rho, double &fl
                 double sv, tol;
                 if (p < m) {
                     double h = 0, sc = fabs(W.c[p]);
-                    #pragma unroll 4
+                    TG_UNROLL_INNER
                     for (int i = 0; i < nq; i++) { const double t = W.A[i * W.lda + p] * W.xq[i]; h += t; sc += fabs(t); }
                     sv = h + W.c[p];
                     tol = 1e-13 * sc;
@@ -506,7 +525,6 @@ TG_HD double tg_violation(const TgSqpWs &W, int meq, const double *weights)
 }
 
 #define TG_SQP_FD_JACOBIAN 1     // flags bit 0: finite-difference emulation instead of analytic derivatives
-#define TG_FD_STEP 1.4901161193847656e-08     // scipy/optimize/_slsqp_py.py:34
 
 // objective and constraints at W.x; with derivs also g and the nonlinear rows of A (analytic)
 template <int D>
@@ -527,29 +545,27 @@ template <int D>
 TG_FN void tg_sqp_fd_derivatives(const TgLayout &L, const int *sp, const double *par, const TgSqpWs &W, double f)
 {
     const int lane = TG_LANE(), n = L.n, m = L.m;
+    // the objective and the light blocks: one perturbed evaluation per variable
     #pragma unroll 1
     for (int i = 0; i < n; i++) {
-        const double xi = W.x[i], lo = W.xl[i], hi = W.xu[i];
-        double h = TG_FD_STEP;
-        const double xt = xi + h;
-        if (xt < lo || xt > hi) {
-            const double ld = xi - lo, ud = hi - xi;
-            if (fabs(h) <= fmax(ld, ud)) h = -h;
-            else h = ud >= ld ? ud : -ld;
-        }
+        const double xi = W.x[i];
+        const double h = tg_fd_step(xi, W.xl[i], W.xu[i]);
         TG_SYNC();
         if (lane == 0) W.x[i] = xi + h;
         TG_SYNC();
         const double dx = W.x[i] - xi;
         const double f1 = tg_objective(L, sp, W.x, 0);
-        tg_constraints_d<D>(L, sp, par, W.x, W.cf, 0, W.scratch);
+        tg_constraints_d<D>(L, sp, par, W.x, W.cf, 0, W.scratch, TG_SKIP_LINEAR | TG_SKIP_TURNING | TG_SKIP_OBSTACLES);
         TG_SYNC();
         if (lane == 0) { W.g[i] = (f1 - f) / dx; W.x[i] = xi; }
         #pragma unroll 1
-        for (int j = lane; j < m; j += TG_NL)
-            if (tg_nlrow(L, j) >= 0) W.A[i * W.lda + j] = (W.cf[j] - W.c[j]) / dx;
+        for (int j = L.r_sder + lane; j < L.r_turn; j += TG_NL) W.A[i * W.lda + j] = (W.cf[j] - W.c[j]) / dx;
         TG_SYNC();
     }
+    // the heavy blocks: item-parallel sweeps (tg_eval.h)
+    if (L.n_turn) tg_fd_turning<D>(L, sp, par, W.x, W.xl, W.xu, W.c[L.r_turn], W.A, W.lda, W.scratch);
+    if (L.n_obs) tg_fd_obstacles<D>(L, par, W.x, W.xl, W.xu, W.c, W.A, W.lda, W.scratch);
+    (void)m;
 }
 
 // ---------------------------------------------------------------------------
@@ -594,18 +610,19 @@ TG_FN void tg_sqp_stage_ls(const TgLayout &L, const int *sp, const double *par, 
     const int lane = TG_LANE(), n = L.n, meq = L.meq;
     TgSqpCtl ctl = *W.ctl;
     const bool fd = (ctl.flags & TG_SQP_FD_JACOBIAN) != 0;
-    if (ctl.state == TG_ST_INIT) {
-        TgJac sink = {W.A, 1, W.lda, 0};
-        tg_linear_jacobian_d<D>(L, sp, par, sink);
-        ctl.f = tg_sqp_evaluate<D>(L, sp, par, W, !fd);
-        ctl.nfev = 1;
-        if (fd) { tg_sqp_fd_derivatives<D>(L, sp, par, W, ctl.f); ctl.nfev += n; }
-        ctl.state = TG_ST_QP;
-    } else if (ctl.state == TG_ST_LS) {
+    const bool init = ctl.state == TG_ST_INIT;
+    if (init || ctl.state == TG_ST_LS) {
+        if (init) {
+            TgJac sink = {W.A, 1, W.lda, 0};
+            tg_linear_jacobian_d<D>(L, sp, par, sink);
+        }
+        // one evaluation at the starting point, or the whole line search on the L1 merit function
         double f;
+        #pragma unroll 1
         for (;;) {
             f = tg_sqp_evaluate<D>(L, sp, par, W, !fd);
             ctl.nfev++;
+            if (init) break;
             const double t = f + tg_violation(W, meq, W.mu);
             const double h1 = t - ctl.t0;
             if (h1 <= ctl.h3 / 10 || ctl.line > 10) break;
@@ -624,14 +641,14 @@ TG_FN void tg_sqp_stage_ls(const TgLayout &L, const int *sp, const double *par, 
             TG_SYNC();
         }
         ctl.f = f;
-        if (trace && lane == 0 && (ctl.iter * (n + 2) <= trace_cap)) {
+        if (!init && trace && lane == 0 && (ctl.iter * (n + 2) <= trace_cap)) {
             double *tr = trace + (ctl.iter - 1) * (n + 2);
             tr[0] = f; tr[1] = ctl.alpha;
             for (int i = 0; i < n; i++) tr[2 + i] = W.x[i];
         }
         // scipy differentiates at the accepted point (mode -1); harmless extra work if the next test ends the run
         if (fd) { tg_sqp_fd_derivatives<D>(L, sp, par, W, f); ctl.nfev += n; }
-        ctl.state = TG_ST_UPDATE;
+        ctl.state = init ? TG_ST_QP : TG_ST_UPDATE;
     }
     TG_SYNC();
     if (lane == 0) *W.ctl = ctl;
