@@ -39,6 +39,7 @@ struct TgSqpCtl {
     double f, f0, t0, h3, h4, alpha, acc;
     double flops;        // algorithmic fp64 operations of the QP stage so far (model counts, see tg_sqp_stage_qp)
     int state, iter, ireset, line, badlin, nfev, status, need_reset, maxiter, flags;
+    int nract;           // rows (< m) with a non-zero multiplier after the last QP: W.ract[0 .. nract)
 };
 enum { TG_ST_INIT = 0, TG_ST_QP, TG_ST_LS, TG_ST_UPDATE, TG_ST_DONE };
 #define TG_CTL_DOUBLES ((int)((sizeof(TgSqpCtl) + 7) / 8))
@@ -51,6 +52,7 @@ struct TgSqpWs {
     // scratch
     double *u, *v, *w, *cf, *Jq, *R, *z, *dq, *rq, *np, *uq, *xq, *hw, *rdi, *scratch;
     int *act, *iact;
+    int *ract;           // persistent: active rows of the last QP, in the order they were added
 };
 
 TG_HD int tg_odd(int v) { return v | 1; }
@@ -94,6 +96,7 @@ TG_HD void tg_sqp_carve4(const TgLayout &L, double *prefix, double *pbase, doubl
     base = pbase;
     TG_TAKE(gl, n1); TG_TAKE(r, w.nc + 1);
     TG_TAKE(Lm, n * n); TG_TAKE(Dd, n1);
+    w.ract = (int *)(base + o); o += (size_t)(n1 / 2 + 1);
     TG_TAKE(A, w.lda * n1);
     if (np_) *np_ = o;
     o = 0; base = sbase;
@@ -376,12 +379,17 @@ TG_QFN void tg_qp_drop(const TgSqpWs &W, int nq, int &iq, int l)
     TG_SYNC();
 }
 
-TG_QFN int tg_qp_solve(const TgSqpWs &W, int nq, int meq, double rho, double &fl)
+TG_QFN int tg_qp_solve(const TgSqpWs &W, int nq, int meq, double rho, double &fl, int &nract)
 {
     const int lane = TG_LANE(), n = W.n, ld = W.ldq, m = W.m;
     const int nc = m + 2 * W.n1;
     const double EPS_DEP = 1e-26;     // |d2|^2 <= EPS_DEP |d|^2 : normal lies in the span of the active ones
-    // ---- J = L^-T D^-1/2 (upper triangular), augmented entry 1/rho
+    // ---- J = L^-T D^-1/2 (upper triangular), augmented entry 1/rho.  L is read n^2/2 times per lane: copy it next
+    //      to J first (the storage of R is free until the first constraint is added)
+    double *Ls = W.R;
+    #pragma unroll 1
+    for (int q = lane; q < n * n; q += TG_NL) Ls[q] = W.Lm[q];
+    TG_SYNC();
     #pragma unroll 1
     for (int k = lane; k < nq; k += TG_NL) {
         double *col = W.Jq + k * ld;
@@ -392,7 +400,7 @@ TG_QFN int tg_qp_solve(const TgSqpWs &W, int nq, int meq, double rho, double &fl
             for (int i = k - 1; i >= 0; i--) {
                 double h = 0;
                 TG_UNROLL_INNER
-                for (int j = i + 1; j <= k; j++) h += W.Lm[i * n + j] * col[j];
+                for (int j = i + 1; j <= k; j++) h += Ls[i * n + j] * col[j];
                 col[i] = -h;
             }
             const double sc = 1 / sqrt(W.Dd[k]);
@@ -437,7 +445,7 @@ TG_QFN int tg_qp_solve(const TgSqpWs &W, int nq, int meq, double rho, double &fl
                 double sv, tol;
                 if (p < m) {
                     double h = 0, sc = fabs(W.c[p]);
-                    TG_UNROLL_INNER
+                    #pragma unroll 8
                     for (int i = 0; i < nq; i++) { const double t = W.A[i * W.lda + p] * W.xq[i]; h += t; sc += fabs(t); }
                     sv = h + W.c[p];
                     tol = 1e-13 * sc;
@@ -457,6 +465,12 @@ TG_QFN int tg_qp_solve(const TgSqpWs &W, int nq, int meq, double rho, double &fl
             if (ip == 0x7fffffff) {
                 #pragma unroll 1
                 for (int k = lane; k < iq; k += TG_NL) W.r[W.act[k]] = W.uq[k];
+                // rows with a (possibly) non-zero multiplier, for the A'r products of the outer iteration
+                int cnt = 0;
+                #pragma unroll 1
+                for (int k = 0; k < iq; k++)
+                    if (W.act[k] < m) { if (lane == 0) W.ract[cnt] = W.act[k]; cnt++; }
+                nract = cnt;
                 TG_SYNC();
                 return TG_QP_OK;
             }
@@ -597,7 +611,7 @@ TG_FN void tg_sqp_begin(const TgLayout &L, const TgSqpWs &W, const double *xin, 
         TgSqpCtl c;
         c.f = 0; c.f0 = 0; c.t0 = 0; c.h3 = 0; c.h4 = 1; c.alpha = 1; c.acc = acc; c.flops = 0;
         c.state = TG_ST_INIT; c.iter = 0; c.ireset = 0; c.line = 0; c.badlin = 0; c.nfev = 0; c.status = -1;
-        c.need_reset = 1; c.maxiter = maxiter; c.flags = flags;
+        c.need_reset = 1; c.maxiter = maxiter; c.flags = flags; c.nract = 0;
         *W.ctl = c;
     }
     TG_SYNC();
@@ -676,8 +690,8 @@ TG_QFN void tg_sqp_stage_qp(const TgLayout &L, const TgSqpWs &W)
             #pragma unroll 1
             for (int i = lane; i < n; i += TG_NL) {
                 double h = W.g[i];
-                #pragma unroll 1
-                for (int j = 0; j < m; j++) h -= W.A[i * W.lda + j] * W.r[j];
+                #pragma unroll 2
+                for (int k = 0; k < ctl.nract; k++) { const int j = W.ract[k]; h -= W.A[i * W.lda + j] * W.r[j]; }
                 W.u[i] = h - W.gl[i];
             }
             TG_SYNC();
@@ -694,7 +708,7 @@ TG_QFN void tg_sqp_stage_qp(const TgLayout &L, const TgSqpWs &W)
                 for (int i = lane; i < n; i += TG_NL) W.u[i] = h4 * W.u[i] + (1 - h4) * W.v[i];
             }
             TG_SYNC();
-            fl += 2.0 * n * m + 6.0 * n * n + 8.0 * n;         // u = grad L - gl ; v = B s ; two rank-one updates of L D L'
+            fl += 2.0 * n * ctl.nract + 6.0 * n * n + 8.0 * n;         // u = grad L - gl ; v = B s ; two rank-one updates of L D L'
             if (h1 == 0 || h2 == 0) ctl.need_reset = 1;
             else {
                 #pragma unroll 1
@@ -741,7 +755,7 @@ TG_QFN void tg_sqp_stage_qp(const TgLayout &L, const TgSqpWs &W)
             double rho = 0;
             #pragma unroll 1
             for (int attempt = 0; attempt < 7; attempt++) {
-                mode = tg_qp_solve(W, nq, meq, rho, fl);
+                mode = tg_qp_solve(W, nq, meq, rho, fl, ctl.nract);
                 if (attempt == 0) {
                     if (mode == 6 && n == meq) mode = 4;
                     if (mode != 4) break;
@@ -769,14 +783,14 @@ TG_QFN void tg_sqp_stage_qp(const TgLayout &L, const TgSqpWs &W)
             #pragma unroll 1
             for (int i = lane; i < n; i += TG_NL) {
                 double h = W.g[i];
-                #pragma unroll 1
-                for (int j = 0; j < m; j++) h -= W.A[i * W.lda + j] * W.r[j];
+                #pragma unroll 2
+                for (int k = 0; k < ctl.nract; k++) { const int j = W.ract[k]; h -= W.A[i * W.lda + j] * W.r[j]; }
                 W.gl[i] = h;
                 W.s[i] = W.xq[i];
                 W.x0[i] = W.x[i];
             }
             ctl.f0 = ctl.f;
-            fl += 2.0 * n * m + 8.0 * m + 4.0 * n;
+            fl += 2.0 * n * ctl.nract + 8.0 * m + 4.0 * n;
             TG_SYNC();
             double gs = 0;
             #pragma unroll 1
