@@ -296,6 +296,19 @@ def main():
     ms_eval = tote.item() / args.steps
     eval_bytes = 8 * (L.n + L.P + L.m + L.m_nl * L.n + 1 + L.n)
 
+    # ---- f1: output sampling of the solved batch (positions, 512 samples per trajectory) -- a pure HBM-write stream
+    from trajectory_generator_b200 import matrix_evaluation as tgs
+    SAMPLES = 512
+    samp = torch.empty((B, L.d, SAMPLES), dtype=torch.float64, device=dev)
+    barrier()
+    ms_s = timed(lambda: tgs.sample_batch((x, L.d, L.N), num_points=SAMPLES, out=samp), args.steps, args.warmup)
+    barrier()
+    tots = torch.tensor([sum(ms_s)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tots, op=dist.ReduceOp.MAX)
+    ms_samp = tots.item() / args.steps
+    samp_bytes = 8 * L.d * SAMPLES * B + 8 * (L.d * L.N) * B
+
     # ---- e2e: host buffers through the C-ABI (tg_solve_host / tg_eval_host), copies inside the timed call
     x_host = bt.x0.copy()
     e2e_times = []
@@ -375,6 +388,12 @@ def main():
                                    "achieved": eval_bytes * B / (ms_eval * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                                    "frac": eval_bytes * B / (ms_eval * 1e-3) / 1e9 / hbm_peak, "traffic": None,
                                    "peak_source": peak_src}},
+            "sampling": {"metric": "trajectory_samples_per_sec", "value": world * B * SAMPLES / (ms_samp * 1e-3),
+                         "unit": "samples/s", "ms_per_step": ms_samp, "samples_per_trajectory": SAMPLES,
+                         "roofline": {"kernel": "tg_sample_kernel", "bound": "hbm",
+                                      "achieved": samp_bytes / (ms_samp * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                                      "frac": samp_bytes / (ms_samp * 1e-3) / 1e9 / hbm_peak, "traffic": None,
+                                      "bytes_per_sample": 8 * L.d, "peak_source": peak_src}},
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "api": "tg_solve_host (C-ABI, host buffers; copies inside the call)"},
             other + "_mode": {"value": world * B / (other_ms * 1e-3), "unit": UNIT, "ms_per_step": other_ms, "steps": 2,

@@ -81,6 +81,23 @@ int tg_eval_host(const int *spec, int B, const double *par, const double *x,
 int tg_solve_host(const int *spec, int B, const double *par, double *x, double *f,
                   int *status, int *nit, int *violation, int maxiter, double ftol, int flags);
 
+/*
+ * Output sampling of a batch of cubic trajectories, device pointers:
+ *   mode 0: matrix_bspline_evaluation_for_dataset / matrix_bspline_derivative_evaluation_for_dataset
+ *           (TG/matrix_evaluation.py:5-33, 104-135): num_points samples over the N-3 intervals of every trajectory;
+ *   mode 1: matrix_bspline_evaluation_for_discrete_steps / ..._derivative_evaluation_for_discrete_steps
+ *           (TG/matrix_evaluation.py:66-102, 137-173): samples every dt from offset[b] (NULL = 0); counts[b] receives
+ *           the number of samples of trajectory b, times[b*capacity + k] (optional) the reference's time_data
+ *           before start_time is added.
+ * Trajectory b: control points row-major d x N at cps + b*cps_stride, scale factor at scale[b*scale_stride]
+ * (so the solver's variable rows x[B][n] can be passed as they are: cps = x, cps_stride = n, scale = x + d*N).
+ * out[(b*d + c)*capacity + k]: coordinate c of sample k, the layout of the reference's spline_data[d, num_points].
+ * derivative_order 0..3.
+ */
+int tg_sample_batch(int d, int N, int B, const double *cps, long cps_stride, const double *scale, long scale_stride,
+                    int derivative_order, int mode, int num_points, const double *offset, double dt,
+                    double *out, long capacity, double *times, int *counts, void *stream);
+
 /* number of kernel launches issued by this library since load (all entry points) */
 unsigned long long tg_launch_count(void);
 

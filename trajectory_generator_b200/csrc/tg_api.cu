@@ -81,6 +81,7 @@ extern "C" int tg_layout(const int *spec, int *out, int cap)
 
 extern "C" const char *tg_last_error(void) { return g_err; }
 extern "C" unsigned long long tg_launch_count(void) { return g_launches.load(); }
+void tg_note_launch(int count) { g_launches += (unsigned long long)count; }
 
 // ---------------------------------------------------------------------------
 // lanes per problem.  Heuristic: enough lanes for the per-interval terms (the longest per-lane chains), capped by

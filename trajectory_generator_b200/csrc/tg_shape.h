@@ -45,6 +45,9 @@ cudaError_t tg_launch_qp_g64(const TgShape &S, int B, double *pws, size_t np, in
                              const int *list, int *next, int parity, int sm_count, cudaStream_t st);
 size_t tg_qp_smem_g64(const TgShape &S, int staged);
 
+// launch counter of the library (tg_launch_count), for kernels launched outside tg_api.cu
+void tg_note_launch(int count);
+
 // fused kernel (group size 32 only)
 cudaError_t tg_launch_fused_g32(const TgShape &S, int B, const double *par, double *x, double *f, int *status, int *nit,
                                 int *violation, int maxiter, double ftol, int flags, double *gws, size_t ws_doubles,
