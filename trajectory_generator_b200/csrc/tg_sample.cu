@@ -2,8 +2,8 @@
 // matrix_bspline_evaluation_for_dataset / ..._derivative_evaluation_for_dataset / ..._for_discrete_steps
 // (TG/matrix_evaluation.py:5-173) for a whole batch of cubic splines.
 //
-// One thread per output sample.  The kernel is a pure stream: it reads d x N control points per trajectory
-// (L1/L2 resident: 4 d doubles feed every sample of an interval) and writes d doubles per sample, coordinate-major
+// A warp takes 64 consecutive samples of one trajectory at a time.  The kernel is a pure stream: it reads d x N control
+// points per trajectory (L1/L2 resident: 4 d doubles feed every sample of an interval) and writes d doubles per sample, coordinate-major
 // [B][d][cap] exactly like the reference's spline_data[d, num_points], so consecutive threads write consecutive
 // 8-byte words.  Bound: HBM writes, 8 d bytes per sample.
 //
@@ -26,6 +26,7 @@ struct SampleArgs {
     int rth;                                   // derivative order 0..3
     int mode;                                  // 0: num_points over [0, N-3] intervals; 1: discrete steps dt from offset[b]
     int num_points;
+    double step0;                              // mode 0: (N-3) / (num_points-1), the step of numpy.linspace
     const double *offset;                      // mode 1: starting offset per trajectory (may be NULL = 0)
     double dt;
     double *out; long cap;                     // out[b][c][k], k < cap
@@ -46,69 +47,78 @@ __device__ __forceinline__ double ipow(double x, int e)
     return e == 0 ? 1.0 : e == 1 ? x : e == 2 ? x * x : x * x * x;
 }
 
+// one sample: trajectory b (control points P, scale sf, derivative weights kd), sample index k
+__device__ __forceinline__ void tg_sample_one(const SampleArgs &a, int b, int k, const double *P, double sf, const double kd[4],
+                                              int num, double step, double off, double last)
+{
+    const int nint = a.N - 3, d = a.d, div = num - 1;
+    const long per = (long)a.cap;
+    double t;            // sample time in units of intervals
+    if (a.mode == 0) {
+        t = (div > 0 && k == div) ? (double)nint : __dmul_rn((double)k, step);          // np.linspace(0, nint, num)
+    } else {
+        const double tdata = (div > 0 && k == div) ? last : __dadd_rn(__dmul_rn((double)k, step), off);
+        if (a.times) a.times[(long)b * per + k] = tdata;
+        t = __ddiv_rn(tdata, sf);
+    }
+    double *o = a.out + ((long)b * d) * per + k;
+    if (!(t >= 0.0) || t > (double)nint) {          // dropped by the reference's masks: the array keeps its zero
+        for (int c = 0; c < d; c++) o[(long)c * per] = 0.0;
+        return;
+    }
+    int i = (int)t;
+    if (i > nint - 1) i = nint - 1;
+    const double tau = t - (double)i;
+    // weights of the four control points: M (K L_r)  (TG/matrix_evaluation.py:26-29, 127-130 with the products
+    // associated as P (M L); the reference forms (P M) L -- the same sums up to the last place)
+    double wl[4], w[4];
+#pragma unroll
+    for (int col = 0; col < 4; col++) w[col] = kd[col] * ipow(tau, 3 - a.rth - col < 0 ? 0 : 3 - a.rth - col);
+#pragma unroll
+    for (int l = 0; l < 4; l++) wl[l] = ((m3(l, 0) * w[0] + m3(l, 1) * w[1]) + m3(l, 2) * w[2]) + m3(l, 3) * w[3];
+    for (int c = 0; c < d; c++) {
+        const double *p = P + c * a.N + i;
+        o[(long)c * per] = ((p[0] * wl[0] + p[1] * wl[1]) + p[2] * wl[2]) + p[3] * wl[3];
+    }
+}
+
+// Work item = (trajectory, chunk of 64 consecutive samples), handed to warps in a grid-stride loop: no block-level
+// synchronisation, two independent samples per lane in flight, coalesced 8-byte stores per coordinate row.
 __global__ void __launch_bounds__(256) tg_sample_kernel(const SampleArgs a)
 {
     const int nint = a.N - 3;
-    const long per = (long)a.cap;
-    // blockIdx.y strides over trajectories, blockIdx.x / threadIdx.x over the samples of one trajectory
-    for (int b = blockIdx.y; b < a.B; b += gridDim.y)
-    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < a.cap; k += gridDim.x * blockDim.x) {
-        const double sf = a.scale ? a.scale[(long)b * a.scale_stride] : 1.0;
-        int num;
-        double t;            // sample time in units of intervals
-        double tdata = 0;    // time_data entry (mode 1)
-        if (a.mode == 0) {
-            num = a.num_points;
-            if (k >= num) continue;
-            // np.linspace(0, nint, num)
-            const int div = num - 1;
-            const double step = div > 0 ? (double)nint / (double)div : 0.0;
-            t = (div > 0 && k == div) ? (double)nint : __dmul_rn((double)k, step);
-        } else {
-            const double off = a.offset ? a.offset[b] : 0.0;
-            const double duration = __dmul_rn(sf, (double)nint);
-            num = (int)(__ddiv_rn(__dsub_rn(duration, off), a.dt)) + 1;          // int((duration - offset) / dt) + 1
-            if (k == 0 && a.counts) a.counts[b] = num;
-            if (k >= num) continue;
-            const double last = __dadd_rn(__dmul_rn((double)(num - 1), a.dt), off);
-            const int div = num - 1;
-            const double step = div > 0 ? __ddiv_rn(__dsub_rn(last, off), (double)div) : 0.0;
-            tdata = (div > 0 && k == div) ? last : __dadd_rn(__dmul_rn((double)k, step), off);
-            if (a.times) a.times[(long)b * per + k] = tdata;
-            t = __ddiv_rn(tdata, sf);
-        }
-        double *o = a.out + ((long)b * a.d) * per + k;
-        if (!(t >= 0.0) || t > (double)nint) {          // dropped by the reference's masks: the array keeps its zero
-            for (int c = 0; c < a.d; c++) o[(long)c * per] = 0.0;
-            continue;
-        }
-        int i = (int)t;
-        if (i > nint - 1) i = nint - 1;
-        const double tau = t - (double)i;
-        // (K L_r)[col] = (3-col)! / (3-r-col)! / sf^r * tau^(3-r-col), col <= 3 - r   (TG/matrix_evaluation.py:175-180)
-        double w[4];
-        const double sr = a.rth == 0 ? 1.0 : a.rth == 1 ? sf : a.rth == 2 ? sf * sf : sf * sf * sf;
-#pragma unroll
-        for (int col = 0; col < 4; col++) {
-            double v = 0.0;
-            if (col <= 3 - a.rth) {
-                double fac = 1.0;
-                for (int q = 0; q < a.rth; q++) fac *= (double)(3 - col - q);
-                v = (a.rth == 0 ? 1.0 : fac / sr) * ipow(tau, 3 - a.rth - col);
-            }
-            w[col] = v;
-        }
+    const int lane = threadIdx.x & 31;
+    const int chunks = (int)((a.cap + 63) / 64);
+    const long items = (long)a.B * chunks;
+    const long warps = (long)gridDim.x * (blockDim.x >> 5);
+    for (long item = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); item < items; item += warps) {
+        const int b = (int)(item / chunks), k0 = (int)(item - (long)b * chunks) * 64;
         const double *P = a.cps + (long)b * a.cps_stride;
-        for (int c = 0; c < a.d; c++) {
-            const double p0 = P[c * a.N + i], p1 = P[c * a.N + i + 1], p2 = P[c * a.N + i + 2], p3 = P[c * a.N + i + 3];
-            double s = 0.0;
+        const double sf = a.scale ? a.scale[(long)b * a.scale_stride] : 1.0;
+        // (K L_r)[col] = (3-col)! / (3-r-col)! / sf^r * tau^(3-r-col), col <= 3 - r   (TG/matrix_evaluation.py:175-180)
+        double kd[4];
+        {
+            const double sr = a.rth == 0 ? 1.0 : a.rth == 1 ? sf : a.rth == 2 ? sf * sf : sf * sf * sf;
 #pragma unroll
             for (int col = 0; col < 4; col++) {
-                const double coef = ((p0 * m3(0, col) + p1 * m3(1, col)) + p2 * m3(2, col)) + p3 * m3(3, col);    // (P M)[c, col]
-                s += coef * w[col];
+                double fac = 1.0;
+                for (int q = 0; q < a.rth; q++) fac *= (double)(3 - col - q);
+                kd[col] = col <= 3 - a.rth ? (a.rth == 0 ? 1.0 : fac / sr) : 0.0;
             }
-            o[(long)c * per] = s;
         }
+        int num = a.num_points;
+        double off = 0, last = 0, step = a.step0;
+        if (a.mode == 1) {
+            off = a.offset ? a.offset[b] : 0.0;
+            const double duration = __dmul_rn(sf, (double)nint);
+            num = (int)(__ddiv_rn(__dsub_rn(duration, off), a.dt)) + 1;          // int((duration - offset) / dt) + 1
+            if (k0 == 0 && lane == 0 && a.counts) a.counts[b] = num;
+            last = __dadd_rn(__dmul_rn((double)(num - 1), a.dt), off);
+            step = num > 1 ? __ddiv_rn(__dsub_rn(last, off), (double)(num - 1)) : 0.0;
+        }
+        const int ka = k0 + lane, kb = k0 + 32 + lane;
+        if (ka < num && ka < a.cap) tg_sample_one(a, b, ka, P, sf, kd, num, step, off, last);
+        if (kb < num && kb < a.cap) tg_sample_one(a, b, kb, P, sf, kd, num, step, off, last);
     }
 }
 
@@ -124,12 +134,16 @@ extern "C" int tg_sample_batch(int d, int N, int B, const double *cps, long cps_
     if ((d != 2 && d != 3) || N < 4 || derivative_order < 0 || derivative_order > 3 || capacity < 1 || !cps || !out ||
         (mode == 0 && (num_points < 1 || num_points > capacity)) || (mode == 1 && !(dt > 0)) || (mode != 0 && mode != 1))
         return 2;
-    SampleArgs a = {d, N, B, cps, cps_stride, scale, scale_stride, derivative_order, mode, num_points, offset, dt, out,
-                    capacity, times, counts};
-    long bx = (capacity + 255) / 256;
-    if (bx > 1024) bx = 1024;
-    const dim3 grid((unsigned)bx, (unsigned)(B < 65535 ? B : 65535));
-    tg_sample_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a);
+    const double step0 = (mode == 0 && num_points > 1) ? (double)(N - 3) / (double)(num_points - 1) : 0.0;
+    SampleArgs a = {d, N, B, cps, cps_stride, scale, scale_stride, derivative_order, mode, num_points, step0, offset, dt,
+                    out, capacity, times, counts};
+
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+    const long items = (long)B * ((capacity + 63) / 64);
+    long blocks = (items + 7) / 8;
+    if (blocks > (long)sms * 8) blocks = (long)sms * 8;
+    tg_sample_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(a);
     tg_note_launch(1);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? 0 : 100 + (int)e;

@@ -379,7 +379,7 @@ TG_QFN void tg_qp_drop(const TgSqpWs &W, int nq, int &iq, int l)
     TG_SYNC();
 }
 
-TG_QFN int tg_qp_solve(const TgSqpWs &W, int nq, int meq, double rho, double &fl, int &nract)
+TG_QFN int tg_qp_solve(const TgSqpWs &W, int nq, int meq, double rho, double &fl, int &nract, double dfloor)
 {
     const int lane = TG_LANE(), n = W.n, ld = W.ldq, m = W.m;
     const int nc = m + 2 * W.n1;
@@ -403,7 +403,7 @@ TG_QFN int tg_qp_solve(const TgSqpWs &W, int nq, int meq, double rho, double &fl
                 for (int j = i + 1; j <= k; j++) h += Ls[i * n + j] * col[j];
                 col[i] = -h;
             }
-            const double sc = 1 / sqrt(W.Dd[k]);
+            const double sc = 1 / sqrt(fmax(W.Dd[k], dfloor));
             for (int i = 0; i <= k; i++) col[i] *= sc;
         } else col[k] = 1 / rho;      // SLSQP's LSQ puts rho itself (not its root) on the diagonal of E: penalty rho^2/2 delta^2
     }
@@ -749,26 +749,35 @@ TG_QFN void tg_sqp_stage_qp(const TgLayout &L, const TgSqpWs &W)
             TG_SYNC();
             ctl.h4 = 1;
             ctl.badlin = 0;
-            // first the QP itself; if its linearised constraints are inconsistent, the augmented problem with one
-            // slack variable (penalty 100, x10 per retry, at most 6 attempts)
+            // attempt 0: the QP itself.  Attempts 1-6 (SLSQP): if its linearised constraints are inconsistent, the
+            // augmented problem with one slack variable, penalty 100, x10 per retry.  Attempt 7 (last resort, departs
+            // from SLSQP, which exits here): the dual active-set method works on the inverse factor L^-T D^-1/2 and
+            // loses the subproblem when D spans ~20 orders of magnitude, where scipy's least-squares chain carries
+            // on; one more try on the augmented problem with D floored at 1e-10 of its largest entry keeps such
+            // problems iterating the way the reference does.
             int mode = 0, nq = n;
-            double rho = 0;
+            double rho = 0, dfloor = 0;
             #pragma unroll 1
-            for (int attempt = 0; attempt < 7; attempt++) {
-                mode = tg_qp_solve(W, nq, meq, rho, fl, ctl.nract);
-                if (attempt == 0) {
-                    if (mode == 6 && n == meq) mode = 4;
-                    if (mode != 4) break;
+            for (int attempt = 0; attempt < 8; attempt++) {
+                if (attempt >= 1 && nq == n) {
                     ctl.badlin = 1;
                     #pragma unroll 1
                     for (int j = lane; j < m; j += TG_NL) W.A[n * W.lda + j] = j < meq ? -W.c[j] : fmax(-W.c[j], 0.0);
                     if (lane == 0) { W.g[n] = 0; W.u[n] = 0; W.v[n] = 1; }
                     TG_SYNC();
-                    nq = n1; rho = 100;
-                } else {
-                    if (mode != 4) break;
-                    rho *= 10;
+                    nq = n1;
                 }
+                if (attempt >= 1) rho = attempt == 1 || attempt == 7 ? 100 : rho * 10;
+                if (attempt == 7) {
+                    double dmax = 0;
+                    #pragma unroll 1
+                    for (int i = 0; i < n; i++) dmax = fmax(dmax, W.Dd[i]);
+                    dfloor = 1e-10 * dmax;
+                }
+                mode = tg_qp_solve(W, nq, meq, rho, fl, ctl.nract, dfloor);
+                if (attempt == 0 && mode == 6 && n == meq) mode = 4;
+                if (mode == TG_QP_OK) break;
+                if (mode != 4 && attempt < 6) attempt = 6;          // exits 6 / 3: straight to the last resort
             }
 #if defined(TG_QP_DEBUG) && !defined(__CUDA_ARCH__)
             {
