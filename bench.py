@@ -296,9 +296,9 @@ def main():
     ms_eval = tote.item() / args.steps
     eval_bytes = 8 * (L.n + L.P + L.m + L.m_nl * L.n + 1 + L.n)
 
-    # ---- f1: output sampling of the solved batch (positions, 512 samples per trajectory) -- a pure HBM-write stream
+    # ---- f1: output sampling of the solved batch (positions, 2048 samples per trajectory) -- a pure HBM-write stream
     from trajectory_generator_b200 import matrix_evaluation as tgs
-    SAMPLES = 512
+    SAMPLES = 2048
     samp = torch.empty((B, L.d, SAMPLES), dtype=torch.float64, device=dev)
     barrier()
     ms_s = timed(lambda: tgs.sample_batch((x, L.d, L.N), num_points=SAMPLES, out=samp), args.steps, args.warmup)

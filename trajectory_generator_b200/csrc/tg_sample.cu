@@ -48,13 +48,14 @@ __device__ __forceinline__ double ipow(double x, int e)
 }
 
 // one sample: trajectory b (control points P, scale sf, derivative weights kd), sample index k
+template <int MODE, int RTH>
 __device__ __forceinline__ void tg_sample_one(const SampleArgs &a, int b, int k, const double *P, double sf, const double kd[4],
                                               int num, double step, double off, double last)
 {
     const int nint = a.N - 3, d = a.d, div = num - 1;
     const long per = (long)a.cap;
     double t;            // sample time in units of intervals
-    if (a.mode == 0) {
+    if (MODE == 0) {
         t = (div > 0 && k == div) ? (double)nint : __dmul_rn((double)k, step);          // np.linspace(0, nint, num)
     } else {
         const double tdata = (div > 0 && k == div) ? last : __dadd_rn(__dmul_rn((double)k, step), off);
@@ -73,7 +74,7 @@ __device__ __forceinline__ void tg_sample_one(const SampleArgs &a, int b, int k,
     // associated as P (M L); the reference forms (P M) L -- the same sums up to the last place)
     double wl[4], w[4];
 #pragma unroll
-    for (int col = 0; col < 4; col++) w[col] = kd[col] * ipow(tau, 3 - a.rth - col < 0 ? 0 : 3 - a.rth - col);
+    for (int col = 0; col < 4; col++) w[col] = col <= 3 - RTH ? (RTH == 0 ? ipow(tau, 3 - col) : kd[col] * ipow(tau, 3 - RTH - col < 0 ? 0 : 3 - RTH - col)) : 0.0;
 #pragma unroll
     for (int l = 0; l < 4; l++) wl[l] = ((m3(l, 0) * w[0] + m3(l, 1) * w[1]) + m3(l, 2) * w[2]) + m3(l, 3) * w[3];
     for (int c = 0; c < d; c++) {
@@ -82,33 +83,35 @@ __device__ __forceinline__ void tg_sample_one(const SampleArgs &a, int b, int k,
     }
 }
 
-// Work item = (trajectory, chunk of 64 consecutive samples), handed to warps in a grid-stride loop: no block-level
-// synchronisation, two independent samples per lane in flight, coalesced 8-byte stores per coordinate row.
+// Work item = (trajectory, chunk of 256 consecutive samples), handed to warps in a grid-stride loop: no block-level
+// synchronisation, the per-trajectory set-up is shared by 8 samples per lane, coalesced 8-byte stores per coordinate row.
+template <int MODE, int RTH>
 __global__ void __launch_bounds__(256) tg_sample_kernel(const SampleArgs a)
 {
     const int nint = a.N - 3;
     const int lane = threadIdx.x & 31;
-    const int chunks = (int)((a.cap + 63) / 64);
+    const int chunks = (int)((a.cap + 255) / 256);
     const long items = (long)a.B * chunks;
     const long warps = (long)gridDim.x * (blockDim.x >> 5);
     for (long item = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); item < items; item += warps) {
-        const int b = (int)(item / chunks), k0 = (int)(item - (long)b * chunks) * 64;
+        const int b = (int)((unsigned)item / (unsigned)chunks), k0 = (int)(item - (long)b * chunks) * 256;
         const double *P = a.cps + (long)b * a.cps_stride;
         const double sf = a.scale ? a.scale[(long)b * a.scale_stride] : 1.0;
         // (K L_r)[col] = (3-col)! / (3-r-col)! / sf^r * tau^(3-r-col), col <= 3 - r   (TG/matrix_evaluation.py:175-180)
         double kd[4];
         {
-            const double sr = a.rth == 0 ? 1.0 : a.rth == 1 ? sf : a.rth == 2 ? sf * sf : sf * sf * sf;
+            const double sr = RTH == 0 ? 1.0 : RTH == 1 ? sf : RTH == 2 ? sf * sf : sf * sf * sf;
 #pragma unroll
             for (int col = 0; col < 4; col++) {
                 double fac = 1.0;
-                for (int q = 0; q < a.rth; q++) fac *= (double)(3 - col - q);
-                kd[col] = col <= 3 - a.rth ? (a.rth == 0 ? 1.0 : fac / sr) : 0.0;
+#pragma unroll
+                for (int q = 0; q < RTH; q++) fac *= (double)(3 - col - q);
+                kd[col] = col <= 3 - RTH ? (RTH == 0 ? 1.0 : fac / sr) : 0.0;
             }
         }
         int num = a.num_points;
         double off = 0, last = 0, step = a.step0;
-        if (a.mode == 1) {
+        if (MODE == 1) {
             off = a.offset ? a.offset[b] : 0.0;
             const double duration = __dmul_rn(sf, (double)nint);
             num = (int)(__ddiv_rn(__dsub_rn(duration, off), a.dt)) + 1;          // int((duration - offset) / dt) + 1
@@ -116,9 +119,9 @@ __global__ void __launch_bounds__(256) tg_sample_kernel(const SampleArgs a)
             last = __dadd_rn(__dmul_rn((double)(num - 1), a.dt), off);
             step = num > 1 ? __ddiv_rn(__dsub_rn(last, off), (double)(num - 1)) : 0.0;
         }
-        const int ka = k0 + lane, kb = k0 + 32 + lane;
-        if (ka < num && ka < a.cap) tg_sample_one(a, b, ka, P, sf, kd, num, step, off, last);
-        if (kb < num && kb < a.cap) tg_sample_one(a, b, kb, P, sf, kd, num, step, off, last);
+        const int kend = num < a.cap ? num : (int)a.cap;
+#pragma unroll 2
+        for (int k = k0 + lane; k < k0 + 256 && k < kend; k += 32) tg_sample_one<MODE, RTH>(a, b, k, P, sf, kd, num, step, off, last);
     }
 }
 
@@ -140,10 +143,18 @@ extern "C" int tg_sample_batch(int d, int N, int B, const double *cps, long cps_
 
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
-    const long items = (long)B * ((capacity + 63) / 64);
+    const long items = (long)B * ((capacity + 255) / 256);
+    if (items > 0x7fffffffL) return 2;
     long blocks = (items + 7) / 8;
     if (blocks > (long)sms * 8) blocks = (long)sms * 8;
-    tg_sample_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(a);
+    cudaStream_t st = (cudaStream_t)stream;
+#define TG_SAMPLE_LAUNCH(M, R) tg_sample_kernel<M, R><<<(int)blocks, 256, 0, st>>>(a)
+#define TG_SAMPLE_MODE(M)                                                                                            \
+    do {                                                                                                             \
+        if (derivative_order == 0) TG_SAMPLE_LAUNCH(M, 0); else if (derivative_order == 1) TG_SAMPLE_LAUNCH(M, 1);   \
+        else if (derivative_order == 2) TG_SAMPLE_LAUNCH(M, 2); else TG_SAMPLE_LAUNCH(M, 3);                         \
+    } while (0)
+    if (mode == 0) TG_SAMPLE_MODE(0); else TG_SAMPLE_MODE(1);
     tg_note_launch(1);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? 0 : 100 + (int)e;
