@@ -14,7 +14,7 @@ struct TgShape {
 // problem indices, handed out through the head_* cursors) and the QP stage appends the problems that are not
 // finished to the other list; `done` counts finished problems (polled by the host).
 struct TgRoundCtl {
-    int count[2], head_ls[2], head_qp[2], done, pad;
+    int count[2], head_ls[2], head_qp[2], head_fd[2], done, pad;
     double flops_qp;      // sum over the chunk's problems of the QP stage's model flop count (written by the finish kernel)
 };
 #define TG_ROUNDCTL_BYTES 256
@@ -39,6 +39,14 @@ struct TgRoundCtl {
 TG_DECLARE_VARIANT(_g8)
 TG_DECLARE_VARIANT(_g16)
 TG_DECLARE_VARIANT(_g32)
+
+// finite-difference stage (tg_solve_fd_g*.cu): value-only evaluators inlined, one kernel of its own
+#define TG_DECLARE_FD(SFX)                                                                                              \
+    cudaError_t tg_launch_fd##SFX(const TgShape &S, int B, const double *par, double *pws, size_t np, size_t smem,      \
+                                  TgRoundCtl *rc, const int *list, int parity, int sm_count, cudaStream_t st);
+TG_DECLARE_FD(_g8)
+TG_DECLARE_FD(_g16)
+TG_DECLARE_FD(_g32)
 
 // QP stage with 64 lanes per problem (tg_solve_g64.cu)
 cudaError_t tg_launch_qp_g64(const TgShape &S, int B, double *pws, size_t np, int staged, size_t smem, TgRoundCtl *rc,

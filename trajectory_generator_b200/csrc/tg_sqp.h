@@ -40,6 +40,7 @@ struct TgSqpCtl {
     double flops;        // algorithmic fp64 operations of the QP stage so far (model counts, see tg_sqp_stage_qp)
     int state, iter, ireset, line, badlin, nfev, status, need_reset, maxiter, flags;
     int nract;           // rows (< m) with a non-zero multiplier after the last QP: W.ract[0 .. nract)
+    int need_fd;         // finite-difference mode: derivatives at the accepted point are still to be formed (stage FD)
 };
 enum { TG_ST_INIT = 0, TG_ST_QP, TG_ST_LS, TG_ST_UPDATE, TG_ST_DONE };
 #define TG_CTL_DOUBLES ((int)((sizeof(TgSqpCtl) + 7) / 8))
@@ -611,7 +612,7 @@ TG_FN void tg_sqp_begin(const TgLayout &L, const TgSqpWs &W, const double *xin, 
         TgSqpCtl c;
         c.f = 0; c.f0 = 0; c.t0 = 0; c.h3 = 0; c.h4 = 1; c.alpha = 1; c.acc = acc; c.flops = 0;
         c.state = TG_ST_INIT; c.iter = 0; c.ireset = 0; c.line = 0; c.badlin = 0; c.nfev = 0; c.status = -1;
-        c.need_reset = 1; c.maxiter = maxiter; c.flags = flags; c.nract = 0;
+        c.need_reset = 1; c.maxiter = maxiter; c.flags = flags; c.nract = 0; c.need_fd = 0;
         *W.ctl = c;
     }
     TG_SYNC();
@@ -661,11 +662,24 @@ TG_FN void tg_sqp_stage_ls(const TgLayout &L, const int *sp, const double *par, 
             for (int i = 0; i < n; i++) tr[2 + i] = W.x[i];
         }
         // scipy differentiates at the accepted point (mode -1); harmless extra work if the next test ends the run
-        if (fd) { tg_sqp_fd_derivatives<D>(L, sp, par, W, f); ctl.nfev += n; }
+        if (fd) ctl.need_fd = 1;          // -> stage FD
         ctl.state = init ? TG_ST_QP : TG_ST_UPDATE;
     }
     TG_SYNC();
     if (lane == 0) *W.ctl = ctl;
+    TG_SYNC();
+}
+
+// stage FD (finite-difference mode only): scipy's forward differences at the point stage LS accepted
+template <int D>
+TG_FN void tg_sqp_stage_fd(const TgLayout &L, const int *sp, const double *par, const TgSqpWs &W)
+{
+    TgSqpCtl ctl = *W.ctl;
+    if (!ctl.need_fd) return;
+    tg_sqp_fd_derivatives<D>(L, sp, par, W, ctl.f);
+    ctl.nfev += L.n; ctl.need_fd = 0;
+    TG_SYNC();
+    if (TG_LANE() == 0) *W.ctl = ctl;
     TG_SYNC();
 }
 
@@ -852,7 +866,7 @@ TG_FN void tg_sqp_solve(const TgLayout &L, const int *sp, const double *par, dou
     for (;;) {
         const int st = W.ctl->state;
         if (st == TG_ST_DONE) break;
-        if (st == TG_ST_INIT || st == TG_ST_LS) tg_sqp_stage_ls<D>(L, sp, par, W, trace, trace_cap);
+        if (st == TG_ST_INIT || st == TG_ST_LS) { tg_sqp_stage_ls<D>(L, sp, par, W, trace, trace_cap); tg_sqp_stage_fd<D>(L, sp, par, W); }
         else tg_sqp_stage_qp(L, W);
     }
     #pragma unroll 1
