@@ -98,6 +98,22 @@ int tg_sample_batch(int d, int N, int B, const double *cps, long cps_stride, con
                     int derivative_order, int mode, int num_points, const double *offset, double dt,
                     double *out, long capacity, double *times, int *counts, void *stream);
 
+/*
+ * Problem construction on the device, device pointers:
+ *   tg_initial_guess_batch: x0[B][n] = [control points | scale0 | waypoint scalars (1) | intermediate times] as
+ *     create_initial_objective_variables builds them (TG/objectives/objective_variables.py:27-48, 63-105) from the
+ *     point sequence seq[B][d][npts] (2 points: straight line; more: equal arc-length steps along the polyline) and,
+ *     with intermediate waypoints, the waypoint locations wseq[B][d][nwp] (nwp = niw + 2).
+ *   tg_sfc_boxes_batch: fits one box per corridor to consecutive points[B][d][ncorr+1]
+ *     (get2D/3DRotationAndTranslationFromPoints, DS/safe_flight_corridor.py:109-146; dimensions = pad[B][ncorr][d]
+ *     + (segment length, 0, 0); SFC.getRotatedBounds, :13-16) and writes [R^T | lower | upper] into the corridor
+ *     slots of the parameter rows par[B][P]; lengths[B][ncorr] (optional) receives the segment lengths.
+ */
+int tg_initial_guess_batch(const int *spec, int B, const double *seq, int npts, const double *wseq, int nwp,
+                           double scale0, double *x0, void *stream);
+int tg_sfc_boxes_batch(const int *spec, int B, const double *points, const double *pad, double *par,
+                       double *lengths, void *stream);
+
 /* number of kernel launches issued by this library since load (all entry points) */
 unsigned long long tg_launch_count(void);
 

@@ -26,7 +26,7 @@ LAYOUT_FIELDS = ("d N nint n ia is0 is1 it0 nws niw meq mineq m r_start n_start 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC"]
 # translation units: the host API (+ legacy single-problem kernels) and one unit per (kernel family, lanes per problem)
-UNITS = ["tg_api.cu", "tg_sample.cu", "tg_solve_fused.cu", "tg_solve_g64.cu"] + ["tg_%s_g%d.cu" % (fam, gs) for fam in ("eval", "solve", "solve_fd") for gs in (8, 16, 32)]
+UNITS = ["tg_api.cu", "tg_sample.cu", "tg_build.cu", "tg_solve_fused.cu", "tg_solve_g64.cu"] + ["tg_%s_g%d.cu" % (fam, gs) for fam in ("eval", "solve", "solve_fd") for gs in (8, 16, 32)]
 HEADERS = ["tg_sqp.h", "tg_eval.h", "tg_spec.h", "tg_shape.h", "tg_kernels_eval.inc", "tg_kernels_solve.inc"]
 
 
@@ -109,6 +109,10 @@ def lib():
                                       ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, ctypes.c_double, vp, ctypes.c_long,
                                       vp, vp, vp]
         L.tg_sample_batch.restype = ctypes.c_int
+        L.tg_initial_guess_batch.argtypes = [_I32, ctypes.c_int, vp, ctypes.c_int, vp, ctypes.c_int, ctypes.c_double, vp, vp]
+        L.tg_initial_guess_batch.restype = ctypes.c_int
+        L.tg_sfc_boxes_batch.argtypes = [_I32, ctypes.c_int, vp, vp, vp, vp, vp]
+        L.tg_sfc_boxes_batch.restype = ctypes.c_int
         for name in ("tg_eval_batch", "tg_linear_rows_batch", "tg_solve_batch", "tg_eval_host", "tg_solve_host"):
             getattr(L, name).restype = ctypes.c_int
         _LIB = L
