@@ -219,7 +219,7 @@ extern "C" size_t tg_solve_workspace_bytes(const int *spec, int B)
     TgSolvePlan P;
     if (tg_make_shape(spec, &S) || tg_plan_solve(S, B, &P)) return 0;
     const size_t phased = P.phased_bytes + tg_lists_bytes(P.chunk);
-    return (P.global_bytes > phased ? P.global_bytes : phased) + TG_ROUNDCTL_BYTES;
+    return (P.global_bytes > phased ? P.global_bytes : phased) + 4 * TG_ROUNDCTL_BYTES;
 }
 
 #define TG_LAUNCH(call, what)                                                   \
@@ -251,17 +251,41 @@ extern "C" int tg_last_solve_stats(double *out, int cap)
     return 6;
 }
 
-// device bookkeeping in front of the per-problem state: [TgRoundCtl | list0[chunk] | list1[chunk]], 256-byte aligned
+// device bookkeeping in front of the per-problem state: [TgRoundCtl x TG_MAX_SLICES | list0[chunk] | list1[chunk]]
+#define TG_MAX_SLICES 4
+#define TG_HEADER_BYTES (TG_MAX_SLICES * TG_ROUNDCTL_BYTES)
 static size_t tg_lists_bytes(int chunk) { return (((size_t)2 * chunk * sizeof(int)) + 255) & ~(size_t)255; }
+
+// A chunk is solved as up to TG_MAX_SLICES independent slices, each with its own round bookkeeping and its own
+// stream: while one slice's stage kernel drains (a round lasts as long as its slowest problem), the other slices'
+// kernels fill the machine.  TG_SLICES overrides the count; stage timing runs one slice (unoverlapped kernels).
+struct TgSliceStreams {
+    cudaStream_t st[TG_MAX_SLICES] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t fork = nullptr, join[TG_MAX_SLICES] = {nullptr, nullptr, nullptr, nullptr};
+    bool ready = false;
+    cudaError_t init()
+    {
+        if (ready) return cudaSuccess;
+        cudaError_t e;
+        if ((e = cudaEventCreateWithFlags(&fork, cudaEventDisableTiming))) return e;
+        for (int i = 0; i < TG_MAX_SLICES; i++) {
+            if ((e = cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking))) return e;
+            if ((e = cudaEventCreateWithFlags(&join[i], cudaEventDisableTiming))) return e;
+        }
+        ready = true;
+        return cudaSuccess;
+    }
+};
+static thread_local TgSliceStreams g_slices;
 
 static int tg_solve_phased(const TgShape &S, const TgSolvePlan &P, int B, const double *par, double *x, double *f,
                            int *status, int *nit, int *violation, int maxiter, double ftol, int flags, void *workspace,
                            cudaStream_t st)
 {
     const TgLayout &L = S.L;
-    TgRoundCtl *rc = (TgRoundCtl *)workspace;
-    int *lists[2] = {(int *)((char *)workspace + TG_ROUNDCTL_BYTES), (int *)((char *)workspace + TG_ROUNDCTL_BYTES) + P.chunk};
-    double *pws = (double *)((char *)workspace + TG_ROUNDCTL_BYTES + tg_lists_bytes(P.chunk));
+    char *wsb = (char *)workspace;
+    int *list_base = (int *)(wsb + TG_HEADER_BYTES);
+    double *pws_base = (double *)(wsb + TG_HEADER_BYTES + tg_lists_bytes(P.chunk));
     const bool timing = g_stage_timing.load() != 0;
     std::vector<cudaEvent_t> ev;
     if (timing) g_stats = TgSolveStats{0, 0, 0, 0, 0, 0};
@@ -273,52 +297,92 @@ static int tg_solve_phased(const TgShape &S, const TgSolvePlan &P, int B, const 
         ev.push_back(e);
         return cudaEventRecord(e, st);
     };
+    int want = 1;          // measured on B200: 2 slices help C2 (-8 %) and cost 3-4 % on C4 / C5
+    if (const char *v = getenv("TG_SLICES")) want = atoi(v);
+    if (want < 1) want = 1;
+    if (want > TG_MAX_SLICES) want = TG_MAX_SLICES;
     for (int lo = 0; lo < B; lo += P.chunk) {
-        const int nb = B - lo < P.chunk ? B - lo : P.chunk;
-        const double *cpar = par + (size_t)lo * L.P;
-        double *cx = x + (size_t)lo * L.n;
-        TG_CUDA(cudaMemsetAsync(rc, 0, TG_ROUNDCTL_BYTES, st));
-        TG_LAUNCH(tg_launch_begin_g32(S, nb, cx, pws, P.np, maxiter, ftol, flags, rc, lists[0], st), "tg_sqp_begin_kernel");
-        int done = 0;
+        const int nbc = B - lo < P.chunk ? B - lo : P.chunk;
+        const int ns = (timing || nbc < 8192) ? 1 : want;
+        if (ns > 1) {
+            TG_CUDA(g_slices.init());
+            TG_CUDA(cudaEventRecord(g_slices.fork, st));
+        }
+        struct Slice { int lo, nb, done; TgRoundCtl *rc; int *lists[2]; double *pws; cudaStream_t st; } sl[TG_MAX_SLICES];
+        for (int k = 0; k < ns; k++) {
+            Slice &q = sl[k];
+            q.lo = (int)((long long)nbc * k / ns);
+            q.nb = (int)((long long)nbc * (k + 1) / ns) - q.lo;
+            q.done = 0;
+            q.rc = (TgRoundCtl *)(wsb + (size_t)k * TG_ROUNDCTL_BYTES);
+            q.lists[0] = list_base + q.lo;
+            q.lists[1] = list_base + P.chunk + q.lo;
+            q.pws = pws_base + (size_t)q.lo * P.np;
+            q.st = ns > 1 ? g_slices.st[k] : st;
+            if (ns > 1) TG_CUDA(cudaStreamWaitEvent(q.st, g_slices.fork, 0));
+            TG_CUDA(cudaMemsetAsync(q.rc, 0, TG_ROUNDCTL_BYTES, q.st));
+            TG_LAUNCH(tg_launch_begin_g32(S, q.nb, x + (size_t)(lo + q.lo) * L.n, q.pws, P.np, maxiter, ftol, flags, q.rc,
+                                          q.lists[0], q.st), "tg_sqp_begin_kernel");
+        }
         // each round = one SLSQP major iteration of every unfinished problem; maxiter + 1 rounds finish everything.
         // Round r works through list r & 1; the QP stage builds the other list from the problems still running.
-        for (int round = 0; round <= maxiter + 1 && done < nb; round++) {
+        for (int round = 0; round <= maxiter + 1; round++) {
             const int par_ = round & 1;
-            TG_CUDA(mark());
-            TG_LAUNCH(TG_DISPATCH(P.gs_ls, tg_launch_ls_g8(S, nb, cpar, pws, P.np, P.smem_ls, rc, lists[par_], par_, g_sm_count, st),
-                                  tg_launch_ls_g16(S, nb, cpar, pws, P.np, P.smem_ls, rc, lists[par_], par_, g_sm_count, st),
-                                  tg_launch_ls_g32(S, nb, cpar, pws, P.np, P.smem_ls, rc, lists[par_], par_, g_sm_count, st)),
-                      "tg_sqp_ls_kernel");
-            if (flags & TG_SOLVE_FD_JACOBIAN)
-                TG_LAUNCH(TG_DISPATCH(P.gs_ls, tg_launch_fd_g8(S, nb, cpar, pws, P.np, P.smem_ls, rc, lists[par_], par_, g_sm_count, st),
-                                      tg_launch_fd_g16(S, nb, cpar, pws, P.np, P.smem_ls, rc, lists[par_], par_, g_sm_count, st),
-                                      tg_launch_fd_g32(S, nb, cpar, pws, P.np, P.smem_ls, rc, lists[par_], par_, g_sm_count, st)),
-                          "tg_sqp_fd_kernel");
-            TG_CUDA(mark());
-            TG_LAUNCH(P.gs_qp == 64 ? tg_launch_qp_g64(S, nb, pws, P.np, P.staged, P.smem_qp, rc, lists[par_], lists[par_ ^ 1], par_, g_sm_count, st) :
-                      TG_DISPATCH(P.gs_qp, tg_launch_qp_g8(S, nb, pws, P.np, P.staged, P.smem_qp, rc, lists[par_], lists[par_ ^ 1], par_, g_sm_count, st),
-                                  tg_launch_qp_g16(S, nb, pws, P.np, P.staged, P.smem_qp, rc, lists[par_], lists[par_ ^ 1], par_, g_sm_count, st),
-                                  tg_launch_qp_g32(S, nb, pws, P.np, P.staged, P.smem_qp, rc, lists[par_], lists[par_ ^ 1], par_, g_sm_count, st)),
-                      "tg_sqp_qp_kernel");
-            TG_CUDA(mark());
+            bool any = false;
+            for (int k = 0; k < ns; k++) {
+                Slice &q = sl[k];
+                if (q.done >= q.nb) continue;
+                any = true;
+                const double *cpar = par + (size_t)(lo + q.lo) * L.P;
+                TG_CUDA(mark());
+                TG_LAUNCH(TG_DISPATCH(P.gs_ls, tg_launch_ls_g8(S, q.nb, cpar, q.pws, P.np, P.smem_ls, q.rc, q.lists[par_], par_, g_sm_count, q.st),
+                                      tg_launch_ls_g16(S, q.nb, cpar, q.pws, P.np, P.smem_ls, q.rc, q.lists[par_], par_, g_sm_count, q.st),
+                                      tg_launch_ls_g32(S, q.nb, cpar, q.pws, P.np, P.smem_ls, q.rc, q.lists[par_], par_, g_sm_count, q.st)),
+                          "tg_sqp_ls_kernel");
+                if (flags & TG_SOLVE_FD_JACOBIAN)
+                    TG_LAUNCH(TG_DISPATCH(P.gs_ls, tg_launch_fd_g8(S, q.nb, cpar, q.pws, P.np, P.smem_ls, q.rc, q.lists[par_], par_, g_sm_count, q.st),
+                                          tg_launch_fd_g16(S, q.nb, cpar, q.pws, P.np, P.smem_ls, q.rc, q.lists[par_], par_, g_sm_count, q.st),
+                                          tg_launch_fd_g32(S, q.nb, cpar, q.pws, P.np, P.smem_ls, q.rc, q.lists[par_], par_, g_sm_count, q.st)),
+                              "tg_sqp_fd_kernel");
+                TG_CUDA(mark());
+                TG_LAUNCH(P.gs_qp == 64 ? tg_launch_qp_g64(S, q.nb, q.pws, P.np, P.staged, P.smem_qp, q.rc, q.lists[par_], q.lists[par_ ^ 1], par_, g_sm_count, q.st) :
+                          TG_DISPATCH(P.gs_qp, tg_launch_qp_g8(S, q.nb, q.pws, P.np, P.staged, P.smem_qp, q.rc, q.lists[par_], q.lists[par_ ^ 1], par_, g_sm_count, q.st),
+                                      tg_launch_qp_g16(S, q.nb, q.pws, P.np, P.staged, P.smem_qp, q.rc, q.lists[par_], q.lists[par_ ^ 1], par_, g_sm_count, q.st),
+                                      tg_launch_qp_g32(S, q.nb, q.pws, P.np, P.staged, P.smem_qp, q.rc, q.lists[par_], q.lists[par_ ^ 1], par_, g_sm_count, q.st)),
+                          "tg_sqp_qp_kernel");
+                TG_CUDA(mark());
+            }
+            if (!any) break;
             if (timing) g_stats.rounds++;
             if ((round & 7) == 7) {      // poll the number of finished problems
-                TG_CUDA(cudaMemcpyAsync(&done, &rc->done, sizeof(int), cudaMemcpyDeviceToHost, st));
-                TG_CUDA(cudaStreamSynchronize(st));
+                for (int k = 0; k < ns; k++)
+                    if (sl[k].done < sl[k].nb)
+                        TG_CUDA(cudaMemcpyAsync(&sl[k].done, &sl[k].rc->done, sizeof(int), cudaMemcpyDeviceToHost, sl[k].st));
+                for (int k = 0; k < ns; k++) TG_CUDA(cudaStreamSynchronize(sl[k].st));
             }
         }
-        TG_LAUNCH(tg_launch_finish_g32(S, nb, pws, P.np, cx, f ? f + lo : nullptr, status ? status + lo : nullptr,
-                                       nit ? nit + lo : nullptr, violation ? violation + lo : nullptr, rc, st),
-                  "tg_sqp_finish_kernel");
+        for (int k = 0; k < ns; k++) {
+            Slice &q = sl[k];
+            const int o = lo + q.lo;
+            TG_LAUNCH(tg_launch_finish_g32(S, q.nb, q.pws, P.np, x + (size_t)o * L.n, f ? f + o : nullptr, status ? status + o : nullptr,
+                                           nit ? nit + o : nullptr, violation ? violation + o : nullptr, q.rc, q.st),
+                      "tg_sqp_finish_kernel");
+            if (ns > 1) {
+                TG_CUDA(cudaEventRecord(g_slices.join[k], q.st));
+                TG_CUDA(cudaStreamWaitEvent(st, g_slices.join[k], 0));
+            }
+        }
         if (timing) {
             double fl = 0;
-            TG_CUDA(cudaMemcpyAsync(&fl, &rc->flops_qp, sizeof(double), cudaMemcpyDeviceToHost, st));
+            TG_CUDA(cudaMemcpyAsync(&fl, &sl[0].rc->flops_qp, sizeof(double), cudaMemcpyDeviceToHost, st));
             TG_CUDA(cudaStreamSynchronize(st));
             g_stats.flops_qp += fl;
+            const bool dump = getenv("TG_DUMP_ROUNDS") != nullptr;
             for (size_t k = 0; k + 3 <= ev.size(); k += 3) {
                 float a = 0, b = 0;
                 cudaEventElapsedTime(&a, ev[k], ev[k + 1]);
                 cudaEventElapsedTime(&b, ev[k + 1], ev[k + 2]);
+                if (dump) fprintf(stderr, "round %3zu: ls+fd %.3f ms  qp %.3f ms\n", k / 3, a, b);
                 g_stats.ms_ls += a; g_stats.ms_qp += b;
                 g_stats.launches_ls++; g_stats.launches_qp++;
             }
@@ -341,7 +405,7 @@ extern "C" int tg_solve_batch(const int *spec, int B, const double *par, double 
     if ((rc = tg_plan_solve(S, B, &P))) return rc;
     if (S.L.n > 62) return tg_fail(3, "more than 62 optimisation variables are not supported by the solve kernel");
     const size_t phased = P.phased_bytes + tg_lists_bytes(P.chunk);
-    const size_t need = (P.global_bytes > phased ? P.global_bytes : phased) + TG_ROUNDCTL_BYTES;
+    const size_t need = (P.global_bytes > phased ? P.global_bytes : phased) + TG_HEADER_BYTES;
     if (!workspace || workspace_bytes < need) return tg_fail(4, "workspace too small (see tg_solve_workspace_bytes)");
     int *counters = (int *)workspace;
     double *gws = (double *)((char *)workspace + 256);

@@ -31,9 +31,15 @@ VARIABLE_LOWER_BOUND = 10e-8     # TG/objectives/objective_variables.py:56 (the 
 class Layout:
     """Row / column / parameter offsets derived from a spec (struct TgLayout of csrc/tg_spec.h)."""
 
+    _cache = {}          # spec bytes -> field dict (a batch of containers shares a handful of shapes)
+
     def __init__(self, spec):
-        for name, value in zip(_native.LAYOUT_FIELDS, _native.layout_ints(spec)):
-            setattr(self, name, int(value))
+        key = np.ascontiguousarray(spec, dtype=np.int32).tobytes()
+        fields = Layout._cache.get(key)
+        if fields is None:
+            fields = {name: int(value) for name, value in zip(_native.LAYOUT_FIELDS, _native.layout_ints(spec))}
+            Layout._cache[key] = fields
+        self.__dict__.update(fields)
 
 
 class PackedProblem:
@@ -192,7 +198,8 @@ def pack_problem(dimension, constraints_container, objective_function_type="mini
         par += [centers.flatten(), np.array([float(o.radius) for o in obstacles])]
 
     par = np.concatenate(par) if par else np.zeros(0)
-    lay = Layout(spec)
+    packed = PackedProblem(spec, None, None, None, None)
+    lay = packed.layout
     if lay.P != par.size:
         raise RuntimeError("parameter row has %d entries, layout expects %d" % (par.size, lay.P))
     n = lay.n
@@ -215,4 +222,5 @@ def pack_problem(dimension, constraints_container, objective_function_type="mini
     if niw:
         xl[lay.it0:] = 0.0
         xu[lay.it0:] = N - 3
-    return PackedProblem(spec, np.ascontiguousarray(par, dtype=np.float64), x0, xl, xu)
+    packed.par, packed.x0, packed.xl, packed.xu = np.ascontiguousarray(par, dtype=np.float64), x0, xl, xu
+    return packed
