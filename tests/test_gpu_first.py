@@ -127,3 +127,32 @@ def test_generate_trajectories_groups_mixed_shapes(native_lib):
         one = gen.generate_trajectory(it[1], **it[2])
         assert res.control_points.shape == one[0].shape
         assert np.array_equal(res.control_points, one[0]) and res.scale_factor == one[1]
+
+
+def test_results_do_not_depend_on_batch_size_or_position(native_lib):
+    """Problems are independent: a problem's answer is bit for bit the same alone, in a ragged batch (sizes that are not
+    multiples of the lane-group / CTA granularity) or behind other problems, in both Jacobian modes; an empty batch is
+    a no-op."""
+    from trajectory_generator_b200 import batch, synthetic as syn
+    for name in ("C2", "C4"):
+        b = syn.make(name, 1000)
+        for mode in ("fd", "analytic"):
+            full = batch.solve_host(b.spec, b.par, b.x0, jacobian=mode)
+            for lo, cnt in ((0, 1), (7, 3), (100, 33), (613, 387)):
+                part = batch.solve_host(b.spec, b.par[lo:lo + cnt], b.x0[lo:lo + cnt], jacobian=mode)
+                assert np.array_equal(part["x"], full["x"][lo:lo + cnt]), (name, mode, lo, cnt)
+                assert np.array_equal(part["status"], full["status"][lo:lo + cnt])
+                assert np.array_equal(part["nit"], full["nit"][lo:lo + cnt])
+        empty = batch.solve_host(b.spec, b.par[:0], b.x0[:0])
+        assert empty["x"].shape == (0, b.layout.n) and empty["status"].shape == (0,)
+
+
+def test_evaluation_of_ragged_batches(native_lib):
+    from trajectory_generator_b200 import batch, synthetic as syn
+    b = syn.make("C3", 77)
+    xe = syn.evaluation_points(b)
+    full = batch.evaluate_host(b.spec, b.par, xe)
+    for lo, cnt in ((0, 1), (5, 13), (40, 37)):
+        part = batch.evaluate_host(b.spec, b.par[lo:lo + cnt], xe[lo:lo + cnt])
+        for k in ("f", "g", "c", "jnl"):
+            assert np.array_equal(part[k], full[k][lo:lo + cnt]), (k, lo, cnt)

@@ -339,11 +339,10 @@ static int tg_solve_phased(const TgShape &S, const TgSolvePlan &P, int B, const 
                                       tg_launch_ls_g16(S, q.nb, cpar, q.pws, P.np, P.smem_ls, q.rc, q.lists[par_], par_, g_sm_count, q.st),
                                       tg_launch_ls_g32(S, q.nb, cpar, q.pws, P.np, P.smem_ls, q.rc, q.lists[par_], par_, g_sm_count, q.st)),
                           "tg_sqp_ls_kernel");
-                if (flags & TG_SOLVE_FD_JACOBIAN)
-                    TG_LAUNCH(TG_DISPATCH(P.gs_ls, tg_launch_fd_g8(S, q.nb, cpar, q.pws, P.np, P.smem_ls, q.rc, q.lists[par_], par_, g_sm_count, q.st),
+                TG_LAUNCH(TG_DISPATCH(P.gs_ls, tg_launch_fd_g8(S, q.nb, cpar, q.pws, P.np, P.smem_ls, q.rc, q.lists[par_], par_, g_sm_count, q.st),
                                           tg_launch_fd_g16(S, q.nb, cpar, q.pws, P.np, P.smem_ls, q.rc, q.lists[par_], par_, g_sm_count, q.st),
                                           tg_launch_fd_g32(S, q.nb, cpar, q.pws, P.np, P.smem_ls, q.rc, q.lists[par_], par_, g_sm_count, q.st)),
-                              "tg_sqp_fd_kernel");
+                          "tg_sqp_der_kernel");
                 TG_CUDA(mark());
                 TG_LAUNCH(P.gs_qp == 64 ? tg_launch_qp_g64(S, q.nb, q.pws, P.np, P.staged, P.smem_qp, q.rc, q.lists[par_], q.lists[par_ ^ 1], par_, g_sm_count, q.st) :
                           TG_DISPATCH(P.gs_qp, tg_launch_qp_g8(S, q.nb, q.pws, P.np, P.staged, P.smem_qp, q.rc, q.lists[par_], q.lists[par_ ^ 1], par_, g_sm_count, q.st),

@@ -4,7 +4,5 @@
 #ifndef TG_NO_INLINE_LS
 #define TG_INLINE_ALL
 #endif
-// ... except the whole-problem evaluators, which the line-search stage calls from several places
-#define TG_SHARED_EVALUATORS
 #define TG_SFX _g16
 #include "tg_kernels_solve.inc"

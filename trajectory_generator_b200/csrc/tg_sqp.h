@@ -40,7 +40,7 @@ struct TgSqpCtl {
     double flops;        // algorithmic fp64 operations of the QP stage so far (model counts, see tg_sqp_stage_qp)
     int state, iter, ireset, line, badlin, nfev, status, need_reset, maxiter, flags;
     int nract;           // rows (< m) with a non-zero multiplier after the last QP: W.ract[0 .. nract)
-    int need_fd;         // finite-difference mode: derivatives at the accepted point are still to be formed (stage FD)
+    int need_der;        // derivatives at the accepted point are still to be formed (stage DER)
 };
 enum { TG_ST_INIT = 0, TG_ST_QP, TG_ST_LS, TG_ST_UPDATE, TG_ST_DONE };
 #define TG_CTL_DOUBLES ((int)((sizeof(TgSqpCtl) + 7) / 8))
@@ -612,7 +612,7 @@ TG_FN void tg_sqp_begin(const TgLayout &L, const TgSqpWs &W, const double *xin, 
         TgSqpCtl c;
         c.f = 0; c.f0 = 0; c.t0 = 0; c.h3 = 0; c.h4 = 1; c.alpha = 1; c.acc = acc; c.flops = 0;
         c.state = TG_ST_INIT; c.iter = 0; c.ireset = 0; c.line = 0; c.badlin = 0; c.nfev = 0; c.status = -1;
-        c.need_reset = 1; c.maxiter = maxiter; c.flags = flags; c.nract = 0; c.need_fd = 0;
+        c.need_reset = 1; c.maxiter = maxiter; c.flags = flags; c.nract = 0; c.need_der = 0;
         *W.ctl = c;
     }
     TG_SYNC();
@@ -635,7 +635,7 @@ TG_FN void tg_sqp_stage_ls(const TgLayout &L, const int *sp, const double *par, 
         double f;
         #pragma unroll 1
         for (;;) {
-            f = tg_sqp_evaluate<D>(L, sp, par, W, !fd);
+            f = tg_sqp_evaluate<D>(L, sp, par, W, false);
             ctl.nfev++;
             if (init) break;
             const double t = f + tg_violation(W, meq, W.mu);
@@ -661,8 +661,9 @@ TG_FN void tg_sqp_stage_ls(const TgLayout &L, const int *sp, const double *par, 
             tr[0] = f; tr[1] = ctl.alpha;
             for (int i = 0; i < n; i++) tr[2 + i] = W.x[i];
         }
-        // scipy differentiates at the accepted point (mode -1); harmless extra work if the next test ends the run
-        if (fd) ctl.need_fd = 1;          // -> stage FD
+        // scipy differentiates at the accepted point only (mode -1) -> stage DER; harmless extra work if the next
+        // test ends the run
+        ctl.need_der = 1;
         ctl.state = init ? TG_ST_QP : TG_ST_UPDATE;
     }
     TG_SYNC();
@@ -670,14 +671,24 @@ TG_FN void tg_sqp_stage_ls(const TgLayout &L, const int *sp, const double *par, 
     TG_SYNC();
 }
 
-// stage FD (finite-difference mode only): scipy's forward differences at the point stage LS accepted
+// stage DER: derivatives at the point stage LS accepted -- the analytic gradient and Jacobian rows (values are
+// recomputed on the way: same numbers), or scipy's forward differences in finite-difference mode
 template <int D>
-TG_FN void tg_sqp_stage_fd(const TgLayout &L, const int *sp, const double *par, const TgSqpWs &W)
+TG_FN void tg_sqp_stage_der(const TgLayout &L, const int *sp, const double *par, const TgSqpWs &W)
 {
     TgSqpCtl ctl = *W.ctl;
-    if (!ctl.need_fd) return;
-    tg_sqp_fd_derivatives<D>(L, sp, par, W, ctl.f);
-    ctl.nfev += L.n; ctl.need_fd = 0;
+    if (!ctl.need_der) return;
+    if (ctl.flags & TG_SQP_FD_JACOBIAN) {
+        tg_sqp_fd_derivatives<D>(L, sp, par, W, ctl.f);
+        ctl.nfev += L.n;
+    } else {
+        const double f = tg_objective(L, sp, W.x, W.g);
+        TgJac sink = {W.A, 1, W.lda, 0};
+        tg_constraints_d<D>(L, sp, par, W.x, W.c, &sink, W.scratch);
+        TG_SYNC();
+        (void)f;
+    }
+    ctl.need_der = 0;
     TG_SYNC();
     if (TG_LANE() == 0) *W.ctl = ctl;
     TG_SYNC();
@@ -866,7 +877,7 @@ TG_FN void tg_sqp_solve(const TgLayout &L, const int *sp, const double *par, dou
     for (;;) {
         const int st = W.ctl->state;
         if (st == TG_ST_DONE) break;
-        if (st == TG_ST_INIT || st == TG_ST_LS) { tg_sqp_stage_ls<D>(L, sp, par, W, trace, trace_cap); tg_sqp_stage_fd<D>(L, sp, par, W); }
+        if (st == TG_ST_INIT || st == TG_ST_LS) { tg_sqp_stage_ls<D>(L, sp, par, W, trace, trace_cap); tg_sqp_stage_der<D>(L, sp, par, W); }
         else tg_sqp_stage_qp(L, W);
     }
     #pragma unroll 1
