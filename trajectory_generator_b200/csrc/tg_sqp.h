@@ -51,12 +51,13 @@ struct TgSqpWs {
     // persistent
     double *x, *xl, *xu, *g, *s, *x0, *gl, *c, *mu, *r, *Lm, *Dd, *A;
     // scratch
-    double *u, *v, *w, *cf, *Jq, *R, *z, *dq, *rq, *np, *uq, *xq, *hw, *rdi, *scratch;
+    double *u, *v, *w, *cf, *Jq, *R, *rsub, *z, *dq, *rq, *np, *uq, *xq, *hw, *rdi, *scratch;
     int *act, *iact;
     int *ract;           // persistent: active rows of the last QP, in the order they were added
 };
 
 TG_HD int tg_odd(int v) { return v | 1; }
+TG_HD int tg_rp(int j) { return j * (j + 1) / 2; }      // offset of column j of the packed upper-triangular R
 
 // unroll factor of the sequential inner products / updates of the QP stage (trip counts are n <= 62)
 #ifndef TG_UNROLL_N
@@ -102,7 +103,8 @@ TG_HD void tg_sqp_carve4(const TgLayout &L, double *prefix, double *pbase, doubl
     if (np_) *np_ = o;
     o = 0; base = sbase;
     TG_TAKE(u, n1); TG_TAKE(v, n1); TG_TAKE(w, n1);
-    TG_TAKE(Jq, w.ldq * n1); TG_TAKE(R, w.ldq * n1);
+    TG_TAKE(Jq, w.ldq * n1);
+    TG_TAKE(R, n1 * (n1 + 1) / 2 + 1); TG_TAKE(rsub, n1);      // R packed by columns (column j: rows 0..j at j(j+1)/2), its sub-diagonal during a drop
     TG_TAKE(z, n1); TG_TAKE(dq, n1); TG_TAKE(rq, n1); TG_TAKE(np, n1); TG_TAKE(uq, n1 + 1); TG_TAKE(xq, n1); TG_TAKE(hw, n1);
     TG_TAKE(rdi, n1);
     double *ints = base + o; o += (size_t)((n1 + 1 + w.nc + 1) / 2 + 1);
@@ -305,7 +307,7 @@ TG_QFN void tg_qp_directions(const TgSqpWs &W, int nq, int iq, double &d2n, doub
         const double rj = W.hw[j] * W.rdi[j];
         if (lane == 0) W.rq[j] = rj;
         #pragma unroll 1
-        for (int k = lane; k < j; k += TG_NL) W.hw[k] -= W.R[j * ld + k] * rj;
+        for (int k = lane; k < j; k += TG_NL) W.hw[k] -= W.R[tg_rp(j) + k] * rj;
         TG_SYNC();
     }
     TG_SYNC();
@@ -333,10 +335,10 @@ TG_QFN void tg_qp_add(const TgSqpWs &W, int nq, int iq, double d2n)
         }
     }
     #pragma unroll 1
-    for (int k = lane; k < iq; k += TG_NL) W.R[iq * ld + k] = W.dq[k];
+    for (int k = lane; k < iq; k += TG_NL) W.R[tg_rp(iq) + k] = W.dq[k];
     if (lane == 0) {
         const double rd = ww > 0 ? sigma : d0;
-        W.R[iq * ld + iq] = rd;
+        W.R[tg_rp(iq) + iq] = rd;
         W.rdi[iq] = 1 / rd;
     }
     TG_SYNC();
@@ -350,24 +352,27 @@ TG_QFN void tg_qp_drop(const TgSqpWs &W, int nq, int &iq, int l)
     #pragma unroll 1
     for (int k = l; k < iq - 1; k++) {
         #pragma unroll 1
-        for (int i = lane; i <= k + 1; i += TG_NL) W.R[k * ld + i] = W.R[(k + 1) * ld + i];
+        for (int i = lane; i <= k + 1; i += TG_NL) {
+            const double e = W.R[tg_rp(k + 1) + i];
+            if (i <= k) W.R[tg_rp(k) + i] = e; else W.rsub[k] = e;          // row k+1 of the shifted column: to be rotated away
+        }
         if (lane == 0) { W.act[k] = W.act[k + 1]; W.uq[k] = W.uq[k + 1]; }
         TG_SYNC();
     }
     iq--;
     #pragma unroll 1
     for (int j = l; j < iq; j++) {
-        double cc = W.R[j * ld + j], ss = W.R[j * ld + j + 1];
+        double cc = W.R[tg_rp(j) + j], ss = W.rsub[j];
         const double h = sqrt(cc * cc + ss * ss);
         TG_SYNC();
         if (h == 0) { if (lane == 0) W.rdi[j] = INFINITY; continue; }
         cc /= h; ss /= h;
-        if (lane == 0) { W.R[j * ld + j] = h; W.R[j * ld + j + 1] = 0; W.rdi[j] = 1 / h; }
+        if (lane == 0) { W.R[tg_rp(j) + j] = h; W.rsub[j] = 0; W.rdi[j] = 1 / h; }
         #pragma unroll 1
         for (int k = j + 1 + lane; k < iq; k += TG_NL) {
-            const double t1 = W.R[k * ld + j], t2 = W.R[k * ld + j + 1];
-            W.R[k * ld + j] = cc * t1 + ss * t2;
-            W.R[k * ld + j + 1] = -ss * t1 + cc * t2;
+            const double t1 = W.R[tg_rp(k) + j], t2 = W.R[tg_rp(k) + j + 1];
+            W.R[tg_rp(k) + j] = cc * t1 + ss * t2;
+            W.R[tg_rp(k) + j + 1] = -ss * t1 + cc * t2;
         }
         #pragma unroll 1
         for (int i = lane; i < nq; i += TG_NL) {
@@ -387,9 +392,14 @@ TG_QFN int tg_qp_solve(const TgSqpWs &W, int nq, int meq, double rho, double &fl
     const double EPS_DEP = 1e-26;     // |d2|^2 <= EPS_DEP |d|^2 : normal lies in the span of the active ones
     // ---- J = L^-T D^-1/2 (upper triangular), augmented entry 1/rho.  L is read n^2/2 times per lane: copy it next
     //      to J first (the storage of R is free until the first constraint is added)
+    // (packed: row i of the copy holds L[i][j], j > i, at i n - i (i + 1) / 2 - i - 1 + j)
     double *Ls = W.R;
     #pragma unroll 1
-    for (int q = lane; q < n * n; q += TG_NL) Ls[q] = W.Lm[q];
+    for (int i = 0; i < n - 1; i++) {
+        const int bi = i * n - i * (i + 1) / 2 - i - 1;
+        #pragma unroll 1
+        for (int j = i + 1 + lane; j < n; j += TG_NL) Ls[bi + j] = W.Lm[i * n + j];
+    }
     TG_SYNC();
     #pragma unroll 1
     for (int k = lane; k < nq; k += TG_NL) {
@@ -400,8 +410,9 @@ TG_QFN int tg_qp_solve(const TgSqpWs &W, int nq, int meq, double rho, double &fl
             #pragma unroll 1
             for (int i = k - 1; i >= 0; i--) {
                 double h = 0;
+                const double *Li = Ls + (i * n - i * (i + 1) / 2 - i - 1);
                 TG_UNROLL_INNER
-                for (int j = i + 1; j <= k; j++) h += Ls[i * n + j] * col[j];
+                for (int j = i + 1; j <= k; j++) h += Li[j] * col[j];
                 col[i] = -h;
             }
             const double sc = 1 / sqrt(fmax(W.Dd[k], dfloor));
