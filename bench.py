@@ -26,7 +26,9 @@ sys.path.insert(0, ROOT)
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one QP-stage launch (round 10, 65,536 problems) from the committed
 # `ncu --set full` captures (profiles/README.md); bytes per launch
-NCU_TRAFFIC = {}
+NCU_TRAFFIC = {"C2": 885.9e6, "C3": 1696.1e6, "C4": 6431.3e6}          # tg_sqp_qp_kernel (profiles/r01_prof_qp_*.raw.csv)
+NCU_TRAFFIC_EVAL = {"C2": 131.4e6}                                     # tg_eval_kernel, 65,536 evaluations
+NCU_TRAFFIC_SAMPLE_PER_SAMPLE = {"C2": 487.3e6 / (65536 * 512)}        # tg_sample_kernel, bytes per sample (d = 2)
 
 METRIC = "optimized_trajectories_per_sec"
 UNIT = "trajectories/s"
@@ -367,7 +369,9 @@ def main():
             # problem: 2 per multiply-add of the factor updates, products and scans it performs) / its launch time.
             "roofline": ({"kernel": "tg_sqp_qp_kernel", "bound": "fp64", "achieved": flops_qp / (ms_qp * 1e-3) / 1e12,
                           "peak": fp64_peak.value, "unit": "TFLOP/s", "frac": flops_qp / (ms_qp * 1e-3) / 1e12 / fp64_peak.value,
-                          "traffic": NCU_TRAFFIC.get(name),
+                          "traffic": NCU_TRAFFIC.get(name) if B == 65536 or name != "C2" else None,
+                          "traffic_note": "dram bytes read + written by ONE launch (round 10 of a 65,536-problem solve) from the "
+                                          "committed ncu --set full capture; the state lives in HBM between stage kernels",
                           "launches_per_step": int(n_qp), "avg_launch_ms": ms_qp / max(n_qp, 1.0),
                           "share_of_step": ms_qp / (ms_ls + ms_qp), "line_search_kernel_ms": ms_ls, "qp_kernel_ms": ms_qp,
                           "algorithmic_flops_per_trajectory": flops_qp / B,
@@ -386,13 +390,16 @@ def main():
                               "d2h_bytes_per_step": 8 * B * (1 + L.n + L.m + L.m_nl * L.n)},
                       "roofline": {"kernel": "tg_eval_kernel", "bound": "hbm",
                                    "achieved": eval_bytes * B / (ms_eval * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                                   "frac": eval_bytes * B / (ms_eval * 1e-3) / 1e9 / hbm_peak, "traffic": None,
+                                   "frac": eval_bytes * B / (ms_eval * 1e-3) / 1e9 / hbm_peak,
+                                   "traffic": NCU_TRAFFIC_EVAL.get(name) if B == 65536 else None,
                                    "peak_source": peak_src}},
             "sampling": {"metric": "trajectory_samples_per_sec", "value": world * B * SAMPLES / (ms_samp * 1e-3),
                          "unit": "samples/s", "ms_per_step": ms_samp, "samples_per_trajectory": SAMPLES,
                          "roofline": {"kernel": "tg_sample_kernel", "bound": "hbm",
                                       "achieved": samp_bytes / (ms_samp * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                                      "frac": samp_bytes / (ms_samp * 1e-3) / 1e9 / hbm_peak, "traffic": None,
+                                      "frac": samp_bytes / (ms_samp * 1e-3) / 1e9 / hbm_peak,
+                                      "traffic": (NCU_TRAFFIC_SAMPLE_PER_SAMPLE[name] * B * SAMPLES
+                                                  if name in NCU_TRAFFIC_SAMPLE_PER_SAMPLE else None),
                                       "bytes_per_sample": 8 * L.d, "peak_source": peak_src}},
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "api": "tg_solve_host (C-ABI, host buffers; copies inside the call)"},
