@@ -142,8 +142,18 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
+def _claim_stdout():
+    """Everything libraries print to fd 1 (e.g. NCCL's version banner on the first collective) goes to stderr;
+    the returned file object is the real stdout, used for the ONE JSON line."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return real
+
+
 def main():
     args = parse()
+    out_stream = _claim_stdout()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -183,7 +193,7 @@ def main():
                                  "status_histogram": {str(k): int(v) for k, v in zip(*np.unique(st, return_counts=True))}},
                 "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
-        print(json.dumps(line))
+        print(json.dumps(line), file=out_stream, flush=True)
         return
 
     # ---------------------------------------------------------------- CUDA path
@@ -448,7 +458,7 @@ def main():
                 "status0_within_1e-3": int(((st_ref == 0) & (st2 == 0) & (np.abs(x2[:, :k] - x_ref[:, :k]).max(1) <= 1e-3)).sum())}
         except Exception as exc:      # the baseline is reported, never required
             line["cpu_baseline"] = {"error": repr(exc)}
-    print(json.dumps(line))
+    print(json.dumps(line), file=out_stream, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
