@@ -47,6 +47,7 @@ enum { TG_ST_INIT = 0, TG_ST_QP, TG_ST_LS, TG_ST_UPDATE, TG_ST_DONE };
 
 struct TgSqpWs {
     int n, n1, m, lda, ldq, nc;      // nc = m + 2*n1 (constraints incl. variable bounds)
+    int sfc0, nsfc, sfc_npts, cpN, cpd;      // corridor rows [sfc0, sfc0 + 2 nsfc): row -> interval -> the only non-zero columns
     TgSqpCtl *ctl;
     // persistent
     double *x, *xl, *xu, *g, *s, *x0, *gl, *c, *mu, *r, *Lm, *Dd, *A;
@@ -88,6 +89,7 @@ TG_HD void tg_sqp_carve4(const TgLayout &L, double *prefix, double *pbase, doubl
     const int n = L.n, n1 = n + 1, m = L.m;
     TgSqpWs w;
     w.n = n; w.n1 = n1; w.m = m; w.lda = tg_odd(m > 0 ? m : 1); w.ldq = tg_odd(n1); w.nc = m + 2 * n1;
+    w.sfc0 = L.r_sfcl; w.nsfc = L.n_sfc; w.sfc_npts = 4 * L.nint; w.cpN = L.N; w.cpd = L.d;
     size_t o = 0;
     double *base = prefix;
 #define TG_TAKE(field, count) w.field = base + o; o += (size_t)(count)
@@ -457,8 +459,24 @@ TG_QFN int tg_qp_solve(const TgSqpWs &W, int nq, int meq, double rho, double &fl
                 double sv, tol;
                 if (p < m) {
                     double h = 0, sc = fabs(W.c[p]);
-                    #pragma unroll 8
-                    for (int i = 0; i < nq; i++) { const double t = W.A[i * W.lda + p] * W.xq[i]; h += t; sc += fabs(t); }
+                    const int q = p - W.sfc0;
+                    if (q >= 0 && q < 2 * W.nsfc) {
+                        // corridor row: only the 4 control points of its interval carry coefficients (tg_jac_sfc), plus
+                        // the slack column of the augmented problem; the skipped terms are exact zeros
+                        const int j = ((q < W.nsfc ? q : q - W.nsfc) % W.sfc_npts) >> 2;
+                        #pragma unroll 1
+                        for (int c = 0; c < W.cpd; c++) {
+                            #pragma unroll
+                            for (int l = 0; l < 4; l++) {
+                                const int i = c * W.cpN + j + l;
+                                const double t = W.A[i * W.lda + p] * W.xq[i]; h += t; sc += fabs(t);
+                            }
+                        }
+                        if (nq > n) { const double t = W.A[n * W.lda + p] * W.xq[n]; h += t; sc += fabs(t); }
+                    } else {
+                        #pragma unroll 8
+                        for (int i = 0; i < nq; i++) { const double t = W.A[i * W.lda + p] * W.xq[i]; h += t; sc += fabs(t); }
+                    }
                     sv = h + W.c[p];
                     tol = 1e-13 * sc;
                 } else {
@@ -473,7 +491,7 @@ TG_QFN int tg_qp_solve(const TgSqpWs &W, int nq, int meq, double rho, double &fl
                 if (sv < -tol && sv < best) { best = sv; ip = p; }
             }
             tg_wargmin(best, ip);
-            fl += 3.0 * (m - meq) * nq;
+            fl += 3.0 * ((m - meq - 2 * W.nsfc) * nq + 2 * W.nsfc * (4 * W.cpd + 1));
             if (ip == 0x7fffffff) {
                 #pragma unroll 1
                 for (int k = lane; k < iq; k += TG_NL) W.r[W.act[k]] = W.uq[k];
