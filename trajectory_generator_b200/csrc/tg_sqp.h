@@ -187,6 +187,8 @@ TG_QFN void tg_ldl_update(int n, double sigma, double *z, double *Lm, double *Dd
     #pragma unroll 1
     for (int i = 0; i < n; i++) {
         const double vv = z[i], di = Dd[i];
+        // the divisions are kept exactly as SLSQP's LDL routine has them (delta = v/d, alpha = t'/t, beta = delta/t'):
+        // replacing them by a carried reciprocal saves 5 % of the stage and moves sensitive solves by 5e-5
         const double delta = vv / di;
         const double tp = sigma < 0 ? w[i] : t + delta * vv;
         const double alpha = tp / t;
