@@ -201,6 +201,14 @@ def main():
     import torch.distributed as dist
     from trajectory_generator_b200 import _native, batch as tgb
     if not torch.cuda.is_available():
+        # a driver that is momentarily busy (seen once right after another process exited) answers "initialization
+        # failed": wait and start over in a fresh process a few times before giving up
+        tries = int(os.environ.get("TG_BENCH_CUDA_RETRY", "0"))
+        if tries < 4:
+            time.sleep(5 + 5 * tries)
+            os.environ["TG_BENCH_CUDA_RETRY"] = str(tries + 1)
+            os.dup2(out_stream.fileno(), 1)
+            os.execv(sys.executable, [sys.executable] + sys.argv)
         raise SystemExit("bench.py: no CUDA device (the product has no CPU path; use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
