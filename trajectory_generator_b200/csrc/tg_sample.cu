@@ -48,11 +48,12 @@ __device__ __forceinline__ double ipow(double x, int e)
 }
 
 // one sample: trajectory b (control points P, scale sf, derivative weights kd), sample index k
-template <int MODE, int RTH>
+template <int MODE, int RTH, int D>
 __device__ __forceinline__ void tg_sample_one(const SampleArgs &a, int b, int k, const double *P, double sf, const double kd[4],
                                               int num, double step, double off, double last)
 {
-    const int nint = a.N - 3, d = a.d, div = num - 1;
+    const int nint = a.N - 3, div = num - 1;
+    constexpr int d = D;
     const long per = (long)a.cap;
     double t;            // sample time in units of intervals
     if (MODE == 0) {
@@ -64,6 +65,7 @@ __device__ __forceinline__ void tg_sample_one(const SampleArgs &a, int b, int k,
     }
     double *o = a.out + ((long)b * d) * per + k;
     if (!(t >= 0.0) || t > (double)nint) {          // dropped by the reference's masks: the array keeps its zero
+#pragma unroll
         for (int c = 0; c < d; c++) o[(long)c * per] = 0.0;
         return;
     }
@@ -77,6 +79,7 @@ __device__ __forceinline__ void tg_sample_one(const SampleArgs &a, int b, int k,
     for (int col = 0; col < 4; col++) w[col] = col <= 3 - RTH ? (RTH == 0 ? ipow(tau, 3 - col) : kd[col] * ipow(tau, 3 - RTH - col < 0 ? 0 : 3 - RTH - col)) : 0.0;
 #pragma unroll
     for (int l = 0; l < 4; l++) wl[l] = ((m3(l, 0) * w[0] + m3(l, 1) * w[1]) + m3(l, 2) * w[2]) + m3(l, 3) * w[3];
+#pragma unroll
     for (int c = 0; c < d; c++) {
         const double *p = P + c * a.N + i;
         o[(long)c * per] = ((p[0] * wl[0] + p[1] * wl[1]) + p[2] * wl[2]) + p[3] * wl[3];
@@ -85,7 +88,7 @@ __device__ __forceinline__ void tg_sample_one(const SampleArgs &a, int b, int k,
 
 // Work item = (trajectory, chunk of 256 consecutive samples), handed to warps in a grid-stride loop: no block-level
 // synchronisation, the per-trajectory set-up is shared by 8 samples per lane, coalesced 8-byte stores per coordinate row.
-template <int MODE, int RTH>
+template <int MODE, int RTH, int D>
 __global__ void __launch_bounds__(256) tg_sample_kernel(const SampleArgs a)
 {
     const int nint = a.N - 3;
@@ -121,7 +124,7 @@ __global__ void __launch_bounds__(256) tg_sample_kernel(const SampleArgs a)
         }
         const int kend = num < a.cap ? num : (int)a.cap;
 #pragma unroll 2
-        for (int k = k0 + lane; k < k0 + 256 && k < kend; k += 32) tg_sample_one<MODE, RTH>(a, b, k, P, sf, kd, num, step, off, last);
+        for (int k = k0 + lane; k < k0 + 256 && k < kend; k += 32) tg_sample_one<MODE, RTH, D>(a, b, k, P, sf, kd, num, step, off, last);
     }
 }
 
@@ -148,7 +151,8 @@ extern "C" int tg_sample_batch(int d, int N, int B, const double *cps, long cps_
     long blocks = (items + 7) / 8;
     if (blocks > (long)sms * 8) blocks = (long)sms * 8;
     cudaStream_t st = (cudaStream_t)stream;
-#define TG_SAMPLE_LAUNCH(M, R) tg_sample_kernel<M, R><<<(int)blocks, 256, 0, st>>>(a)
+#define TG_SAMPLE_LAUNCH(M, R)                                                                                       \
+    do { if (d == 2) tg_sample_kernel<M, R, 2><<<(int)blocks, 256, 0, st>>>(a); else tg_sample_kernel<M, R, 3><<<(int)blocks, 256, 0, st>>>(a); } while (0)
 #define TG_SAMPLE_MODE(M)                                                                                            \
     do {                                                                                                             \
         if (derivative_order == 0) TG_SAMPLE_LAUNCH(M, 0); else if (derivative_order == 1) TG_SAMPLE_LAUNCH(M, 1);   \
