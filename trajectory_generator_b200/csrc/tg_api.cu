@@ -200,9 +200,13 @@ static int tg_plan_solve(const TgShape &S, int B, TgSolvePlan *P)
     P->gs_qp = gs;
     const size_t with_state = gs == 64 ? tg_qp_smem_g64(S, 1) : TG_DISPATCH(gs, tg_qp_smem_g8(S, 1), tg_qp_smem_g16(S, 1), tg_qp_smem_g32(S, 1));
     const size_t without = gs == 64 ? tg_qp_smem_g64(S, 0) : TG_DISPATCH(gs, tg_qp_smem_g8(S, 0), tg_qp_smem_g16(S, 0), tg_qp_smem_g32(S, 0));
-    P->staged = with_state * 4 <= sm_total - 4096;
-    if (const char *v = getenv("TG_QP_STAGED")) P->staged = atoi(v) != 0 && with_state <= budget;      // tuning override
-    P->smem_qp = P->staged ? with_state : without;
+    const size_t with_prefix = gs == 64 ? tg_qp_smem_g64(S, 2) : TG_DISPATCH(gs, tg_qp_smem_g8(S, 2), tg_qp_smem_g16(S, 2), tg_qp_smem_g32(S, 2));
+    P->staged = with_state * 4 <= sm_total - 4096 ? 1 : with_prefix * 4 <= sm_total - 4096 ? 2 : 0;
+    if (const char *v = getenv("TG_QP_STAGED")) {      // tuning override
+        const int want = atoi(v);
+        P->staged = want == 1 && with_state <= budget ? 1 : want == 2 && with_prefix <= budget ? 2 : 0;
+    }
+    P->smem_qp = P->staged == 1 ? with_state : P->staged == 2 ? with_prefix : without;
     if (P->smem_qp > budget) return tg_fail(3, "problem shape too large for the QP kernel's shared memory");
     size_t chunk = TG_PHASED_CHUNK_BYTES / (P->np * sizeof(double));
     if (chunk < 1024) chunk = 1024;

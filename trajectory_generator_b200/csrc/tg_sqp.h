@@ -51,8 +51,10 @@ struct TgSqpWs {
     TgSqpCtl *ctl;
     // persistent
     double *x, *xl, *xu, *g, *s, *x0, *gl, *c, *mu, *r, *Lm, *Dd, *A;
+    double *rot;         // persistent: rotation (d x d, row-major) of the corridor that owns each interval, written once by stage LS
     // scratch
     double *u, *v, *w, *cf, *Jq, *R, *rsub, *z, *dq, *rq, *np, *uq, *xq, *hw, *rdi, *scratch;
+    double *rotq;        // scratch: copy of rot for the violation scans of the QP stage
     int *act, *iact;
     int *ract;           // persistent: active rows of the last QP, in the order they were added
 };
@@ -77,7 +79,7 @@ TG_HD int tg_rp(int j) { return j * (j + 1) / 2; }      // offset of column j of
 #define TG_QFN TG_FN
 #endif
 
-// Carves the per-problem state.  The persistent block is [ctl | x xl xu g s x0 | c mu | gl r Lm Dd | A]; its first
+// Carves the per-problem state.  The persistent block is [ctl | x xl xu g s x0 | c mu | gl r Lm Dd | ract rot | A]; its first
 // `npre` doubles (everything the line-search stage touches except A) may be staged at `prefix` while the rest
 // stays at `pbase` (+ offset) -- pass prefix == pbase for one contiguous block.  The scratch block is
 // [QP-stage scratch | evaluation scratch (cf, evaluators' scratch)]; `ebase` != 0 places the evaluation scratch
@@ -101,6 +103,7 @@ TG_HD void tg_sqp_carve4(const TgLayout &L, double *prefix, double *pbase, doubl
     TG_TAKE(gl, n1); TG_TAKE(r, w.nc + 1);
     TG_TAKE(Lm, n * n); TG_TAKE(Dd, n1);
     w.ract = (int *)(base + o); o += (size_t)(n1 / 2 + 1);
+    TG_TAKE(rot, L.n_sfc ? L.nint * L.d * L.d : 0);
     TG_TAKE(A, w.lda * n1);
     if (np_) *np_ = o;
     o = 0; base = sbase;
@@ -109,6 +112,7 @@ TG_HD void tg_sqp_carve4(const TgLayout &L, double *prefix, double *pbase, doubl
     TG_TAKE(R, n1 * (n1 + 1) / 2 + 1); TG_TAKE(rsub, n1);      // R packed by columns (column j: rows 0..j at j(j+1)/2), its sub-diagonal during a drop
     TG_TAKE(z, n1); TG_TAKE(dq, n1); TG_TAKE(rq, n1); TG_TAKE(np, n1); TG_TAKE(uq, n1 + 1); TG_TAKE(xq, n1); TG_TAKE(hw, n1);
     TG_TAKE(rdi, n1);
+    TG_TAKE(rotq, L.n_sfc ? L.nint * L.d * L.d : 0);
     double *ints = base + o; o += (size_t)((n1 + 1 + w.nc + 1) / 2 + 1);
     w.act = (int *)ints; w.iact = w.act + n1 + 1;
     if (nsq_) *nsq_ = o;
@@ -455,30 +459,60 @@ TG_QFN int tg_qp_solve(const TgSqpWs &W, int nq, int meq, double rho, double &fl
         if (!eq) {
             double best = 0;
             ip = 0x7fffffff;
+            if (W.nsfc) {
+                // corridor rows (lb <= R' Q <= ub, CF/sfc_constraints.py:53-77) through the hull points: lane item =
+                // (interval j, hull point k); Q = MINVO point of the step's control points, then the d rotated
+                // coordinates serve the d lower and d upper rows of that point -- 4 d + d^2 products for 2 d rows
+                // instead of 2 d row products of 4 d terms read from A.  (The row that is picked is re-evaluated from
+                // A by tg_qp_value; the scan only ranks violations.)
+                const int npts = W.sfc_npts, D = W.cpd, N = W.cpN;
+                const double slack = nq > n ? W.xq[n] : 0.0;
+                #pragma unroll 1
+                for (int q = lane; q < npts; q += TG_NL) {
+                    const int j = q >> 2, k = q & 3;
+                    const double m0 = tg_minvo_py(0, k), m1 = tg_minvo_py(1, k), m2 = tg_minvo_py(2, k), m3 = tg_minvo_py(3, k);
+                    double Q[3], Qa[3];
+                    #pragma unroll
+                    for (int c = 0; c < 3; c++) {
+                        Q[c] = 0; Qa[c] = 0;
+                        if (c < D) {
+                            const double *xp = W.xq + c * N + j;
+                            const double t0 = xp[0] * m0, t1 = xp[1] * m1, t2 = xp[2] * m2, t3 = xp[3] * m3;
+                            Q[c] = t0 + t1 + t2 + t3;
+                            Qa[c] = fabs(t0) + fabs(t1) + fabs(t2) + fabs(t3);
+                        }
+                    }
+                    const double *rot = W.rotq + j * D * D;
+                    #pragma unroll
+                    for (int rr = 0; rr < 3; rr++) {
+                        if (rr >= D) continue;
+                        double sq = 0, sa = 0;
+                        #pragma unroll
+                        for (int c = 0; c < 3; c++)
+                            if (c < D) { const double rc = rot[rr * D + c]; sq += rc * Q[c]; sa += fabs(rc) * Qa[c]; }
+                        #pragma unroll
+                        for (int side = 0; side < 2; side++) {
+                            const int p = W.sfc0 + side * W.nsfc + rr * npts + q;
+                            if (W.iact[p]) continue;
+                            const double cp = W.c[p];
+                            double h = side ? -sq : sq, sc = fabs(cp) + sa;
+                            if (nq > n) { const double t = W.A[n * W.lda + p] * slack; h += t; sc += fabs(t); }
+                            const double sv = h + cp;
+                            if (sv < -1e-13 * sc && (sv < best || (sv == best && p < ip))) { best = sv; ip = p; }
+                        }
+                    }
+                }
+            }
+            const int nskip = 2 * W.nsfc;                 // the other rows and the bounds
             #pragma unroll 1
-            for (int p = meq + lane; p < nc; p += TG_NL) {
+            for (int t = meq + lane; t < nc - nskip; t += TG_NL) {
+                const int p = t >= W.sfc0 ? t + nskip : t;
                 if (W.iact[p]) continue;
                 double sv, tol;
                 if (p < m) {
                     double h = 0, sc = fabs(W.c[p]);
-                    const int q = p - W.sfc0;
-                    if (q >= 0 && q < 2 * W.nsfc) {
-                        // corridor row: only the 4 control points of its interval carry coefficients (tg_jac_sfc), plus
-                        // the slack column of the augmented problem; the skipped terms are exact zeros
-                        const int j = ((q < W.nsfc ? q : q - W.nsfc) % W.sfc_npts) >> 2;
-                        #pragma unroll 1
-                        for (int c = 0; c < W.cpd; c++) {
-                            #pragma unroll
-                            for (int l = 0; l < 4; l++) {
-                                const int i = c * W.cpN + j + l;
-                                const double t = W.A[i * W.lda + p] * W.xq[i]; h += t; sc += fabs(t);
-                            }
-                        }
-                        if (nq > n) { const double t = W.A[n * W.lda + p] * W.xq[n]; h += t; sc += fabs(t); }
-                    } else {
-                        #pragma unroll 8
-                        for (int i = 0; i < nq; i++) { const double t = W.A[i * W.lda + p] * W.xq[i]; h += t; sc += fabs(t); }
-                    }
+                    #pragma unroll 8
+                    for (int i = 0; i < nq; i++) { const double t = W.A[i * W.lda + p] * W.xq[i]; h += t; sc += fabs(t); }
                     sv = h + W.c[p];
                     tol = 1e-13 * sc;
                 } else {
@@ -490,10 +524,10 @@ TG_QFN int tg_qp_solve(const TgSqpWs &W, int nq, int meq, double rho, double &fl
                     sv = q < W.n1 ? W.xq[i] - bnd : bnd - W.xq[i];
                     tol = 1e-13 * (fabs(bnd) + fabs(W.xq[i]));
                 }
-                if (sv < -tol && sv < best) { best = sv; ip = p; }
+                if (sv < -tol && (sv < best || (sv == best && p < ip))) { best = sv; ip = p; }
             }
             tg_wargmin(best, ip);
-            fl += 3.0 * ((m - meq - 2 * W.nsfc) * nq + 2 * W.nsfc * (4 * W.cpd + 1));
+            fl += 3.0 * ((m - meq - 2 * W.nsfc) * nq + W.sfc_npts * (4 * W.cpd + W.cpd * W.cpd)) + 4.0 * W.nsfc;
             if (ip == 0x7fffffff) {
                 #pragma unroll 1
                 for (int k = lane; k < iq; k += TG_NL) W.r[W.act[k]] = W.uq[k];
@@ -661,6 +695,14 @@ TG_FN void tg_sqp_stage_ls(const TgLayout &L, const int *sp, const double *par, 
         if (init) {
             TgJac sink = {W.A, 1, W.lda, 0};
             tg_linear_jacobian_d<D>(L, sp, par, sink);
+            // rotation of the corridor that owns each interval, for the QP stage's violation scans
+            if (L.n_sfc) {
+                #pragma unroll 1
+                for (int q = lane; q < L.nint * D * D; q += TG_NL) {
+                    const int j = q / (D * D);
+                    W.rot[q] = par[L.p_sfc + tg_corridor_of_interval(sp, j) * tg_sfc_stride(D) + (q - j * D * D)];
+                }
+            }
         }
         // one evaluation at the starting point, or the whole line search on the L1 merit function
         double f;
@@ -775,6 +817,11 @@ TG_QFN void tg_sqp_stage_qp(const TgLayout &L, const TgSqpWs &W)
         }
     }
     if (ctl.state == TG_ST_QP) {
+        if (W.nsfc) {
+            #pragma unroll 1
+            for (int q = lane; q < (W.sfc_npts >> 2) * W.cpd * W.cpd; q += TG_NL) W.rotq[q] = W.rot[q];
+            TG_SYNC();
+        }
         do {
             if (ctl.need_reset) {
                 // ---- reset the BFGS factor to the identity
