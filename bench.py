@@ -355,6 +355,30 @@ def main():
         else:
             te.append(time.perf_counter() - t)
     eval_e2e = world * B / float(np.mean(te))
+    # ---- f3: problems of different shapes in ONE call (tg_solve_mixed_host: the buckets' solves overlap on the
+    #      device, each on its own stream) against bucket-by-bucket tg_solve_host calls; host buffers, end to end
+    mixed = None
+    if world == 1:
+        MB = 4096
+        gens = (("C2", synthetic.make_c2, 2), ("C3", synthetic.make_c3, 3), ("C4", synthetic.make_c4, 4))
+        mbs = [g(MB, seed=synthetic.SEED0 + k + 100 * r) for _, g, k in gens for r in (1, 2)]
+        mbs += [synthetic.make_c5(MB, kind, seed=synthetic.SEED0 + 5 + 100 * r) for kind in ("angular_rate", "curvature") for r in (1,)]
+        buckets = [(b.spec, b.par, b.x0) for b in mbs]
+        runs = {"bucket_by_bucket": lambda: [tgb.solve_host(sp_, p_, x_, jacobian=args.jacobian) for sp_, p_, x_ in buckets],
+                "one_call": lambda: tgb.solve_mixed_host(buckets, jacobian=args.jacobian)}
+        tm, res_m = {}, {}
+        for label, fn in runs.items():
+            fn()
+            ts = []
+            for _ in range(2):
+                t = time.perf_counter(); res_m[label] = fn(); ts.append(time.perf_counter() - t)
+            tm[label] = min(ts)
+        same = all(np.array_equal(a["x"], b["x"]) and np.array_equal(a["status"], b["status"])
+                   for a, b in zip(res_m["bucket_by_bucket"], res_m["one_call"]))
+        mixed = {"workload": "%d buckets of %d problems: C2, C3, C4 (two seeds each), C5a, C5c" % (len(buckets), MB),
+                 "problems": MB * len(buckets), "unit": UNIT, "api": "tg_solve_mixed_host (C-ABI, host buffers)",
+                 "one_call": MB * len(buckets) / tm["one_call"], "bucket_by_bucket": MB * len(buckets) / tm["bucket_by_bucket"],
+                 "identical_results": bool(same)}
     if rank == 0:
         sampler.stop_flag = True
         sampler.join(timeout=2)
@@ -426,6 +450,8 @@ def main():
                               "status_histogram": {str(k): int(v) for k, v in zip(*np.unique(other_status, return_counts=True))}},
             "gpu_launches": int(solve_launches),
             "clocks": sampler.summary()}
+    if mixed is not None:
+        line["mixed_shapes"] = mixed
 
     # ---- CPU baseline on the box's host cores (rank 0, N = 1 only): bounded sample of the same problems
     if world == 1 and not args.no_cpu_baseline and cpu_path_available():

@@ -82,6 +82,19 @@ int tg_solve_host(const int *spec, int B, const double *par, double *x, double *
                   int *status, int *nit, int *violation, int maxiter, double ftol, int flags);
 
 /*
+ * Problems of DIFFERENT shapes in one call.  The reference derives the number of control
+ * points and the corridor split of every problem from its geometry (TG/trajectory_generator.py:148-162,
+ * DS/safe_flight_corridor.py:78-88), so a set of ConstraintsContainers is a mix of shapes; the caller groups
+ * them into `nbuckets` buckets by shape descriptor.  specs = nbuckets x tg_spec_count() ints; counts[k] problems
+ * in bucket k; par[k], x[k], f[k], status[k], nit[k], violation[k] = that bucket's HOST arrays, laid out as for
+ * tg_solve_host (f / status / nit / violation, or single entries of them, may be NULL).  Buckets are solved
+ * concurrently, each on its own stream; results are those of tg_solve_host on every bucket.
+ */
+int tg_solve_mixed_host(int nbuckets, const int *specs, const int *counts, const double *const *par,
+                        double *const *x, double *const *f, int *const *status, int *const *nit,
+                        int *const *violation, int maxiter, double ftol, int flags);
+
+/*
  * Output sampling of a batch of cubic trajectories, device pointers:
  *   mode 0: matrix_bspline_evaluation_for_dataset / matrix_bspline_derivative_evaluation_for_dataset
  *           (TG/matrix_evaluation.py:5-33, 104-135): num_points samples over the N-3 intervals of every trajectory;

@@ -146,3 +146,45 @@ def solve_host(spec, par, x0, maxiter=100, ftol=1e-6, jacobian="analytic", fused
                                      _np_ptr(viol), int(maxiter), float(ftol), _flags(jacobian, fused))
     _native.check(rc, "tg_solve_host")
     return dict(x=x, f=f, status=status, nit=nit, violation=viol)
+
+
+def solve_mixed_host(buckets, maxiter=100, ftol=1e-6, jacobian="analytic"):
+    """Host-buffer M2 solve of problems of DIFFERENT shapes in one call (tg_solve_mixed_host).
+    buckets: list of (spec, par[Bk,P], x0[Bk,n]).  Buckets run concurrently on the device, each on its own stream.
+    Returns one dict(x, f, status, nit, violation) of numpy arrays per bucket, in input order."""
+    L = _native.lib()
+    nb = len(buckets)
+    if nb == 0:
+        return []
+    nspec = L.tg_spec_count()
+    specs = np.zeros((nb, nspec), dtype=np.int32)
+    counts = np.zeros(nb, dtype=np.int32)
+    keep, outs = [], []
+    vp_array = ctypes.c_void_p * nb
+    ptrs = {k: vp_array() for k in ("par", "x", "f", "status", "nit", "violation")}
+    for k, (spec, par, x0) in enumerate(buckets):
+        lay = Layout(spec)
+        spec = np.ascontiguousarray(spec, dtype=np.int32)
+        if spec.size != nspec:
+            raise ValueError("spec must have %d entries" % nspec)
+        specs[k] = spec
+        par = np.ascontiguousarray(par, dtype=np.float64).reshape(-1, lay.P)
+        x = np.array(x0, dtype=np.float64).reshape(-1, lay.n)
+        B = x.shape[0]
+        if par.shape[0] != B:
+            raise ValueError("bucket %d: %d parameter rows for %d problems" % (k, par.shape[0], B))
+        counts[k] = B
+        out = dict(x=x, f=np.empty(B), status=np.empty(B, dtype=np.int32), nit=np.empty(B, dtype=np.int32),
+                   violation=np.empty(B, dtype=np.int32))
+        keep.append(par)
+        outs.append(out)
+        ptrs["par"][k] = par.ctypes.data
+        for name in ("x", "f", "status", "nit", "violation"):
+            ptrs[name][k] = out[name].ctypes.data
+    L.tg_solve_mixed_host.restype = ctypes.c_int
+    L.tg_solve_mixed_host.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_void_p] * 6 + \
+                                     [ctypes.c_int, ctypes.c_double, ctypes.c_int]
+    rc = L.tg_solve_mixed_host(nb, specs.ctypes.data, counts.ctypes.data, ptrs["par"], ptrs["x"], ptrs["f"], ptrs["status"],
+                               ptrs["nit"], ptrs["violation"], int(maxiter), float(ftol), _flags(jacobian, False))
+    _native.check(rc, "tg_solve_mixed_host")
+    return outs

@@ -13,6 +13,9 @@
 #include <string.h>
 #include <mutex>
 #include <atomic>
+#include <string>
+#include <thread>
+#include <vector>
 
 #include "tg_sqp.h"
 #include "tg_shape.h"
@@ -200,13 +203,9 @@ static int tg_plan_solve(const TgShape &S, int B, TgSolvePlan *P)
     P->gs_qp = gs;
     const size_t with_state = gs == 64 ? tg_qp_smem_g64(S, 1) : TG_DISPATCH(gs, tg_qp_smem_g8(S, 1), tg_qp_smem_g16(S, 1), tg_qp_smem_g32(S, 1));
     const size_t without = gs == 64 ? tg_qp_smem_g64(S, 0) : TG_DISPATCH(gs, tg_qp_smem_g8(S, 0), tg_qp_smem_g16(S, 0), tg_qp_smem_g32(S, 0));
-    const size_t with_prefix = gs == 64 ? tg_qp_smem_g64(S, 2) : TG_DISPATCH(gs, tg_qp_smem_g8(S, 2), tg_qp_smem_g16(S, 2), tg_qp_smem_g32(S, 2));
-    P->staged = with_state * 4 <= sm_total - 4096 ? 1 : with_prefix * 4 <= sm_total - 4096 ? 2 : 0;
-    if (const char *v = getenv("TG_QP_STAGED")) {      // tuning override
-        const int want = atoi(v);
-        P->staged = want == 1 && with_state <= budget ? 1 : want == 2 && with_prefix <= budget ? 2 : 0;
-    }
-    P->smem_qp = P->staged == 1 ? with_state : P->staged == 2 ? with_prefix : without;
+    P->staged = with_state * 4 <= sm_total - 4096;
+    if (const char *v = getenv("TG_QP_STAGED")) P->staged = atoi(v) != 0 && with_state <= budget;      // tuning override
+    P->smem_qp = P->staged ? with_state : without;
     if (P->smem_qp > budget) return tg_fail(3, "problem shape too large for the QP kernel's shared memory");
     size_t chunk = TG_PHASED_CHUNK_BYTES / (P->np * sizeof(double));
     if (chunk < 1024) chunk = 1024;
@@ -548,6 +547,99 @@ extern "C" int tg_solve_host(const int *spec, int B, const double *par, double *
     if (nit) TG_CUDA(cudaMemcpyAsync(nit, di + B, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, 0));
     if (violation) TG_CUDA(cudaMemcpyAsync(violation, di + 2 * B, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, 0));
     TG_CUDA(cudaStreamSynchronize(0));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// f3: problems of DIFFERENT shapes in one call.  The reference chooses the number of control
+// points and the corridor split from the geometry (TG/trajectory_generator.py:148-162), so a real workload is a
+// mix of shapes.  The caller hands over the buckets (problems grouped by shape descriptor); up to
+// TG_MIXED_WORKERS buckets are in flight at a time, each on its own stream with its own device buffers, so that
+// the lock-step rounds of one bucket fill the SMs that the tail of another bucket's round leaves idle.
+// ---------------------------------------------------------------------------
+#define TG_MIXED_WORKERS 4
+
+struct TgMixedSlot {
+    cudaStream_t st = nullptr;
+    DevBuf par, x, f, i, ws;
+};
+static std::mutex g_mixed_mutex;
+static TgMixedSlot g_mixed[TG_MIXED_WORKERS];
+
+extern "C" int tg_solve_mixed_host(int nbuckets, const int *specs, const int *counts, const double *const *par,
+                                   double *const *x, double *const *f, int *const *status, int *const *nit,
+                                   int *const *violation, int maxiter, double ftol, int flags)
+{
+    if (nbuckets <= 0) return 0;
+    if (!specs || !counts || !par || !x) return tg_fail(1, "tg_solve_mixed_host: NULL argument");
+    int rc = tg_device_check();
+    if (rc) return rc;
+    int dev = 0;
+    TG_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(g_mixed_mutex);
+    // validate every bucket before any work is queued
+    for (int k = 0; k < nbuckets; k++) {
+        TgShape S;
+        if ((rc = tg_make_shape(specs + (size_t)k * TG_SP_COUNT, &S))) return rc;
+        if (counts[k] > 0 && (!par[k] || !x[k])) return tg_fail(1, "tg_solve_mixed_host: NULL bucket buffer");
+    }
+    const int workers = nbuckets < TG_MIXED_WORKERS ? nbuckets : TG_MIXED_WORKERS;
+    for (int w = 0; w < workers; w++)
+        if (!g_mixed[w].st) TG_CUDA(cudaStreamCreateWithFlags(&g_mixed[w].st, cudaStreamNonBlocking));
+    // largest buckets first: the long solves start early and the small ones fill in around them
+    std::vector<int> order(nbuckets);
+    for (int k = 0; k < nbuckets; k++) order[k] = k;
+    for (int a = 1; a < nbuckets; a++)
+        for (int b = a; b > 0 && counts[order[b]] > counts[order[b - 1]]; b--) { int t = order[b]; order[b] = order[b - 1]; order[b - 1] = t; }
+    std::atomic<int> cursor{0};
+    std::vector<int> rcs(workers, 0);
+    std::vector<std::string> errs(workers);
+    auto work = [&](int w) {
+        cudaSetDevice(dev);
+        TgMixedSlot &s = g_mixed[w];
+        for (;;) {
+            const int at = cursor.fetch_add(1);
+            if (at >= nbuckets) break;
+            const int k = order[at], B = counts[k];
+            if (B <= 0) continue;
+            const int *spec = specs + (size_t)k * TG_SP_COUNT;
+            TgShape S;
+            tg_make_shape(spec, &S);
+            const TgLayout &L = S.L;
+            const size_t nb = sizeof(double);
+            const size_t wsb = tg_solve_workspace_bytes(spec, B);
+            int r = wsb ? 0 : tg_fail(5, g_err[0] ? g_err : "cannot plan the solve kernel");
+            if (!r) r = s.par.ensure((size_t)B * (L.P + 1) * nb);
+            if (!r) r = s.x.ensure((size_t)B * L.n * nb);
+            if (!r) r = s.f.ensure((size_t)B * nb);
+            if (!r) r = s.i.ensure((size_t)B * 3 * sizeof(int));
+            if (!r) r = s.ws.ensure(wsb);
+            int *di = (int *)s.i.p;
+            auto cp = [&](void *dst, const void *src, size_t bytes, cudaMemcpyKind kind) {
+                if (r) return;
+                cudaError_t e = cudaMemcpyAsync(dst, src, bytes, kind, s.st);
+                if (e != cudaSuccess) r = tg_fail(100 + (int)e, "cudaMemcpyAsync", e);
+            };
+            cp(s.par.p, par[k], (size_t)B * L.P * nb, cudaMemcpyHostToDevice);
+            cp(s.x.p, x[k], (size_t)B * L.n * nb, cudaMemcpyHostToDevice);
+            if (!r) r = tg_solve_batch(spec, B, (const double *)s.par.p, (double *)s.x.p, (double *)s.f.p, di, di + B, di + 2 * B,
+                                       maxiter, ftol, flags, s.ws.p, wsb, s.st);
+            cp(x[k], s.x.p, (size_t)B * L.n * nb, cudaMemcpyDeviceToHost);
+            if (f && f[k]) cp(f[k], s.f.p, (size_t)B * nb, cudaMemcpyDeviceToHost);
+            if (status && status[k]) cp(status[k], di, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost);
+            if (nit && nit[k]) cp(nit[k], di + B, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost);
+            if (violation && violation[k]) cp(violation[k], di + 2 * B, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost);
+            cudaError_t e = cudaStreamSynchronize(s.st);
+            if (!r && e != cudaSuccess) r = tg_fail(100 + (int)e, "cudaStreamSynchronize", e);
+            if (r) { rcs[w] = r; errs[w] = g_err; break; }
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int w = 1; w < workers; w++) pool.emplace_back(work, w);
+    work(0);
+    for (std::thread &t : pool) t.join();
+    for (int w = 0; w < workers; w++)
+        if (rcs[w]) return tg_fail(rcs[w], errs[w].c_str());
     return 0;
 }
 

@@ -19,6 +19,32 @@ struct TgRoundCtl {
 };
 #define TG_ROUNDCTL_BYTES 256
 
+// Every kernel with dynamic shared memory is allowed the device's opt-in maximum (not the size of the launch at
+// hand: launches of one kernel with different sizes may be issued from several host threads, tg_solve_mixed_host).
+// Done once per (device, kernel).
+#include <mutex>
+#include <set>
+#include <utility>
+template <typename K>
+static inline cudaError_t tg_allow_shared_memory(K kernel)
+{
+    static std::mutex mu;
+    static std::set<std::pair<int, const void *>> done;
+    int dev = 0, optin = 0;
+    cudaError_t e;
+    if ((e = cudaGetDevice(&dev))) return e;
+    std::lock_guard<std::mutex> lock(mu);
+    const std::pair<int, const void *> key(dev, (const void *)kernel);
+    if (done.count(key)) return cudaSuccess;
+    cudaFuncAttributes attr;
+    if ((e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev))) return e;
+    if ((e = cudaFuncGetAttributes(&attr, kernel))) return e;
+    // static + dynamic <= the opt-in limit
+    if ((e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)attr.sharedSizeBytes))) return e;
+    done.insert(key);
+    return cudaSuccess;
+}
+
 #define TG_DECLARE_VARIANT(SFX)                                                                                           \
     cudaError_t tg_launch_eval##SFX(const TgShape &S, int B, const double *par, const double *x, double *f, double *g,    \
                                     double *c, double *jnl, int sm_count, int smem_optin, cudaStream_t st);               \

@@ -54,11 +54,11 @@ cudaError_t tg_launch_fused_g32(const TgShape &S, int B, const double *par, doub
 {
     cudaError_t e;
     if (S.L.d == 2) {
-        if ((e = cudaFuncSetAttribute(tg_solve_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))) return e;
+        if ((e = tg_allow_shared_memory(tg_solve_kernel<2>))) return e;
         tg_solve_kernel<2><<<ctas, warps_per_cta * 32, smem, st>>>(S, B, par, x, f, status, nit, violation, maxiter, ftol,
                                                                     flags, gws, ws_doubles, warps_per_cta, queue);
     } else {
-        if ((e = cudaFuncSetAttribute(tg_solve_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))) return e;
+        if ((e = tg_allow_shared_memory(tg_solve_kernel<3>))) return e;
         tg_solve_kernel<3><<<ctas, warps_per_cta * 32, smem, st>>>(S, B, par, x, f, status, nit, violation, maxiter, ftol,
                                                                     flags, gws, ws_doubles, warps_per_cta, queue);
     }

@@ -3,7 +3,8 @@
 ``generate_trajectory`` keeps the reference signature and return value
 ``(control_points[d,N], scale_factor, is_violation)``; the SLSQP loop and everything it evaluates
 run on the GPU (one warp per problem).  ``generate_trajectories`` is the batched addition: many
-containers at once, grouped by problem shape, one kernel launch per group.
+containers at once, grouped by problem shape; the groups are solved in one library call, concurrently on
+the device (tg_solve_mixed_host).
 """
 import numpy as np
 
@@ -74,12 +75,15 @@ class TrajectoryGenerator:
         for i, p in enumerate(packed):
             groups.setdefault(p.key, []).append(i)
         results = [None] * count
-        for idx in groups.values():
-            first = packed[idx[0]]
-            par = np.stack([packed[i].par for i in idx])
-            x0 = np.stack([np.clip(packed[i].x0, packed[i].xl, packed[i].xu) for i in idx])
-            out = batch.solve_host(first.spec, par, x0, self._maxiter, self._ftol, self._jacobian)
-            lay = first.layout
+        order = list(groups.values())
+        buckets = [(packed[idx[0]].spec, np.stack([packed[i].par for i in idx]),
+                    np.stack([np.clip(packed[i].x0, packed[i].xl, packed[i].xu) for i in idx])) for idx in order]
+        if len(buckets) == 1:
+            outs = [batch.solve_host(*buckets[0], self._maxiter, self._ftol, self._jacobian)]
+        else:       # different shapes: one call, the buckets' solves overlap on the device (tg_solve_mixed_host)
+            outs = batch.solve_mixed_host(buckets, self._maxiter, self._ftol, self._jacobian)
+        for idx, out in zip(order, outs):
+            lay = packed[idx[0]].layout
             for k, i in enumerate(idx):
                 x = out["x"][k]
                 cps = np.reshape(x[:lay.d * lay.N], (lay.d, lay.N)).copy()
