@@ -157,67 +157,93 @@ TG_HD bool tg_finite(double v) { return v - v == 0; }
 // ---------------------------------------------------------------------------
 // LDL^T rank-one update  B <- B + sigma z z^T  (composite-t method of Fletcher &
 // Powell, as used by SLSQP's LDL routine).  Lm: unit lower factor, column i at
-// Lm[i*n + j] (j > i); Dd: diagonal.  z is destroyed; w is scratch.
+// Lm[i*n + j] (j > i); Dd: diagonal.  z is destroyed; w is scratch (n), sc is
+// scratch (5 n).
+//
+// SLSQP's loop over the columns carries three divisions per column (delta = v/d,
+// alpha = t'/t, beta = delta/t') behind the recurrence v <- v - v_i L_i.  The
+// same numbers are formed here in three phases so that no division sits on a
+// serial path: (A) the recurrence alone -- v = L^-1 z, one step per column;
+// (B) the scalars of every column at once, one column per lane (the only serial
+// part left is the chain t' = t + delta v of multiply-adds; for sigma < 0 the
+// forward / backward sums of v^2/d); (C) the columns of L, one per lane, each
+// lane re-running its own entry of the recurrence (same operations, same
+// order: bit-identical to the one-loop form).
 // ---------------------------------------------------------------------------
-TG_QFN void tg_ldl_update(int n, double sigma, double *z, double *Lm, double *Dd, double *w)
+#ifdef __CUDA_ARCH__
+#define TG_MULADD2(a, b, c, d) fma((a), (b), __dmul_rn((c), (d)))      // a b + c d, contracted the way the one-loop form was
+#else
+#define TG_MULADD2(a, b, c, d) ((a) * (b) + (c) * (d))
+#endif
+TG_QFN void tg_ldl_update(int n, double sigma, double *z, double *Lm, double *Dd, double *w, double *sc)
 {
     const int lane = TG_LANE();
     if (sigma == 0) return;
+    double *vf = w, *dl = sc, *tpv = sc + n, *al = sc + 2 * n, *be = sc + 3 * n, *ga = sc + 4 * n;
     double t = 1 / sigma;
-    if (sigma < 0) {
+    // ---- A: vf = L^-1 z
+    #pragma unroll 1
+    for (int i = lane; i < n; i += TG_NL) vf[i] = z[i];
+    TG_SYNC();
+    #pragma unroll 1
+    for (int i = 0; i < n - 1; i++) {
+        const double vv = vf[i];
         #pragma unroll 1
-        for (int i = lane; i < n; i += TG_NL) w[i] = z[i];
-        TG_SYNC();
-        #pragma unroll 1
-        for (int i = 0; i < n; i++) {
-            const double vv = w[i];
-            t += vv * vv / Dd[i];
-            #pragma unroll 1
-            for (int j = i + 1 + lane; j < n; j += TG_NL) w[j] -= vv * Lm[i * n + j];
-            TG_SYNC();
-        }
-        if (t >= 0) t = DBL_EPSILON / sigma;
-        if (lane == 0) {
-            #pragma unroll 1
-            for (int i = n - 1; i >= 0; i--) {
-                const double uu = w[i];
-                w[i] = t;
-                t -= uu * uu / Dd[i];
-            }
-        }
-        t = tg_bcast(t, 0);
+        for (int j = i + 1 + lane; j < n; j += TG_NL) vf[j] -= vv * Lm[i * n + j];
         TG_SYNC();
     }
+    // ---- B: delta_i = v_i / d_i ; t'_i ; alpha_i = t'_i / t_i, beta_i = delta_i / t'_i, gamma_i = t_i / t'_i
     #pragma unroll 1
-    for (int i = 0; i < n; i++) {
-        const double vv = z[i], di = Dd[i];
-        // the divisions are kept exactly as SLSQP's LDL routine has them (delta = v/d, alpha = t'/t, beta = delta/t'):
-        // replacing them by a carried reciprocal saves 5 % of the stage and moves sensitive solves by 5e-5
-        const double delta = vv / di;
-        const double tp = sigma < 0 ? w[i] : t + delta * vv;
-        const double alpha = tp / t;
-        const double dnew = alpha * di;            // written after the step's barrier (every lane has read Dd[i] by then)
-        if (i < n - 1) {
-            const double beta = delta / tp;
-            if (alpha > 4) {
-                const double gamma = t / tp;
-                #pragma unroll 1
-                for (int j = i + 1 + lane; j < n; j += TG_NL) {
-                    const double uu = Lm[i * n + j];
-                    Lm[i * n + j] = gamma * uu + beta * z[j];
-                    z[j] -= vv * uu;
-                }
+    for (int i = lane; i < n; i += TG_NL) {
+        const double vv = vf[i], di = Dd[i];
+        dl[i] = vv / di;
+        if (sigma < 0) al[i] = vv * vv / di;
+    }
+    TG_SYNC();
+    const double tstart = sigma < 0 ? 0 : t;
+    if (sigma < 0) {
+        #pragma unroll 1
+        for (int i = 0; i < n; i++) t += al[i];
+        if (t >= 0) t = DBL_EPSILON / sigma;
+        #pragma unroll 1
+        for (int i = n - 1; i >= 0; i--) {
+            if (lane == 0) tpv[i] = t;
+            t -= al[i];
+        }
+    } else {
+        #pragma unroll 1
+        for (int i = 0; i < n; i++) {
+            t = t + dl[i] * vf[i];
+            if (lane == 0) tpv[i] = t;
+        }
+    }
+    const double t0 = sigma < 0 ? t : tstart;            // t before column 0
+    TG_SYNC();
+    #pragma unroll 1
+    for (int i = lane; i < n; i += TG_NL) {
+        const double tp = tpv[i], ti = i ? tpv[i - 1] : t0;
+        const double alpha = tp / ti;
+        be[i] = dl[i] / tp;
+        ga[i] = ti / tp;
+        al[i] = alpha;
+        Dd[i] = alpha * Dd[i];
+    }
+    TG_SYNC();
+    // ---- C: column j of L and its own entry of the recurrence
+    #pragma unroll 1
+    for (int j = 1 + lane; j < n; j += TG_NL) {
+        double zj = z[j];
+        #pragma unroll 2
+        for (int i = 0; i < j; i++) {
+            const double uu = Lm[i * n + j], vv = vf[i], beta = be[i];
+            if (al[i] > 4) {
+                Lm[i * n + j] = TG_MULADD2(ga[i], uu, beta, zj);
+                zj -= vv * uu;
             } else {
-                #pragma unroll 1
-                for (int j = i + 1 + lane; j < n; j += TG_NL) {
-                    z[j] -= vv * Lm[i * n + j];
-                    Lm[i * n + j] += beta * z[j];
-                }
+                zj -= vv * uu;
+                Lm[i * n + j] = uu + beta * zj;
             }
         }
-        t = tp;
-        TG_SYNC();
-        if (lane == 0) Dd[i] = dnew;
     }
     TG_SYNC();
 }
@@ -811,7 +837,7 @@ TG_QFN void tg_sqp_stage_qp(const TgLayout &L, const TgSqpWs &W)
             else {
                 #pragma unroll 1
                 for (int pass = 0; pass < 2; pass++)
-                    tg_ldl_update(n, pass == 0 ? 1 / h1 : -1 / h2, pass == 0 ? W.u : W.v, W.Lm, W.Dd, W.w);
+                    tg_ldl_update(n, pass == 0 ? 1 / h1 : -1 / h2, pass == 0 ? W.u : W.v, W.Lm, W.Dd, W.w, W.Jq);
             }
             ctl.state = TG_ST_QP;
         }
