@@ -300,7 +300,9 @@ static int tg_solve_phased(const TgShape &S, const TgSolvePlan &P, int B, const 
         ev.push_back(e);
         return cudaEventRecord(e, st);
     };
-    int want = 1;          // measured on B200: 2 slices help C2 (-8 %) and cost 3-4 % on C4 / C5
+    // measured on B200 (65,536 problems): two slices -9.5 % on C2 (short stage kernels, a long tail of rounds with few
+    // problems), -2 % on C3, +3 % on C5a, +8 % on C4 (state in L2 / HBM): two when the state is staged in shared memory
+    int want = P.staged ? 2 : 1;
     if (const char *v = getenv("TG_SLICES")) want = atoi(v);
     if (want < 1) want = 1;
     if (want > TG_MAX_SLICES) want = TG_MAX_SLICES;

@@ -77,6 +77,18 @@
 #define TG_NL 1
 #define TG_SYNC() ((void)0)
 #endif
+// Serial recurrences with a group sync per step (back substitutions, the forward substitution of the factor update):
+// a 64-lane group runs them on its first warp alone -- a warp sync per step instead of a named barrier between two
+// warps -- and meets at one TG_SYNC() afterwards.  Same arithmetic, same order.
+#if defined(__CUDA_ARCH__) && TG_GS == 64
+#define TG_SERIAL_LANES 32
+#define TG_SERIAL_ACTIVE() (TG_LANE() < 32)
+#define TG_SERIAL_SYNC() __syncwarp()
+#else
+#define TG_SERIAL_LANES TG_NL
+#define TG_SERIAL_ACTIVE() true
+#define TG_SERIAL_SYNC() TG_SYNC()
+#endif
 
 // ---------------------------------------------------------------------------
 // group folds (identity on the host build)

@@ -185,13 +185,16 @@ TG_QFN void tg_ldl_update(int n, double sigma, double *z, double *Lm, double *Dd
     #pragma unroll 1
     for (int i = lane; i < n; i += TG_NL) vf[i] = z[i];
     TG_SYNC();
-    #pragma unroll 1
-    for (int i = 0; i < n - 1; i++) {
-        const double vv = vf[i];
+    if (TG_SERIAL_ACTIVE()) {
         #pragma unroll 1
-        for (int j = i + 1 + lane; j < n; j += TG_NL) vf[j] -= vv * Lm[i * n + j];
-        TG_SYNC();
+        for (int i = 0; i < n - 1; i++) {
+            const double vv = vf[i];
+            #pragma unroll 1
+            for (int j = i + 1 + lane; j < n; j += TG_SERIAL_LANES) vf[j] -= vv * Lm[i * n + j];
+            TG_SERIAL_SYNC();
+        }
     }
+    TG_SYNC();
     // ---- B: delta_i = v_i / d_i ; t'_i ; alpha_i = t'_i / t_i, beta_i = delta_i / t'_i, gamma_i = t_i / t'_i
     #pragma unroll 1
     for (int i = lane; i < n; i += TG_NL) {
@@ -336,13 +339,15 @@ TG_QFN void tg_qp_directions(const TgSqpWs &W, int nq, int iq, double &d2n, doub
         W.z[i] = h;
     }
     // back substitution R rq = d1 (column oriented; hw holds the running right-hand side, rdi = 1 / diag R)
-    #pragma unroll 1
-    for (int j = iq - 1; j >= 0; j--) {
-        const double rj = W.hw[j] * W.rdi[j];
-        if (lane == 0) W.rq[j] = rj;
+    if (TG_SERIAL_ACTIVE()) {
         #pragma unroll 1
-        for (int k = lane; k < j; k += TG_NL) W.hw[k] -= W.R[tg_rp(j) + k] * rj;
-        TG_SYNC();
+        for (int j = iq - 1; j >= 0; j--) {
+            const double rj = W.hw[j] * W.rdi[j];
+            if (lane == 0) W.rq[j] = rj;
+            #pragma unroll 1
+            for (int k = lane; k < j; k += TG_SERIAL_LANES) W.hw[k] -= W.R[tg_rp(j) + k] * rj;
+            TG_SERIAL_SYNC();
+        }
     }
     TG_SYNC();
 }
@@ -529,9 +534,11 @@ TG_QFN int tg_qp_solve(const TgSqpWs &W, int nq, int meq, double rho, double &fl
                     }
                 }
             }
-            const int nskip = 2 * W.nsfc;                 // the other rows and the bounds
+            // the other rows and the bounds, handed out from the last lane down: the dense rows come first and land on
+            // the lanes (of a 64-lane group: on the warp) that the hull points above leave idle
+            const int nskip = 2 * W.nsfc;
             #pragma unroll 1
-            for (int t = meq + lane; t < nc - nskip; t += TG_NL) {
+            for (int t = meq + (TG_NL - 1 - lane); t < nc - nskip; t += TG_NL) {
                 const int p = t >= W.sfc0 ? t + nskip : t;
                 if (W.iact[p]) continue;
                 double sv, tol;
