@@ -24,11 +24,12 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-# dram__bytes_read.sum + dram__bytes_write.sum of one QP-stage launch (round 10, 65,536 problems) from the committed
-# `ncu --set full` captures (profiles/README.md); bytes per launch
-NCU_TRAFFIC = {"C2": 885.9e6, "C3": 1696.1e6, "C4": 6431.3e6}          # tg_sqp_qp_kernel (profiles/r01_prof_qp_*.raw.csv)
-NCU_TRAFFIC_EVAL = {"C2": 131.4e6}                                     # tg_eval_kernel, 65,536 evaluations
-NCU_TRAFFIC_SAMPLE_PER_SAMPLE = {"C2": 487.3e6 / (65536 * 512)}        # tg_sample_kernel, bytes per sample (d = 2)
+# dram__bytes_read.sum + dram__bytes_write.sum of the QP-stage kernel working through 65,536 problems in round 10 of a
+# solve, from the committed `ncu --set full` captures (profiles/README.md).  C2 runs as two slices: the captured
+# launch covers 32,768 problems and moves 417.2 MB; the figure below is per 65,536 problems like the others.
+NCU_TRAFFIC = {"C2": 2 * 417.2e6, "C3": 1693.5e6, "C4": 4035.6e6}      # tg_sqp_qp_kernel (profiles/r01_prof_qp_*.raw.csv)
+NCU_TRAFFIC_EVAL = {"C2": 150.9e6}                                     # tg_eval_kernel, 65,536 evaluations
+NCU_TRAFFIC_SAMPLE_PER_SAMPLE = {"C2": 486.3e6 / (65536 * 512)}        # tg_sample_kernel, bytes per sample (d = 2)
 
 METRIC = "optimized_trajectories_per_sec"
 UNIT = "trajectories/s"
@@ -412,7 +413,7 @@ def main():
             "roofline": ({"kernel": "tg_sqp_qp_kernel", "bound": "fp64", "achieved": flops_qp / (ms_qp * 1e-3) / 1e12,
                           "peak": fp64_peak.value, "unit": "TFLOP/s", "frac": flops_qp / (ms_qp * 1e-3) / 1e12 / fp64_peak.value,
                           "traffic": NCU_TRAFFIC.get(name) if B == 65536 or name != "C2" else None,
-                          "traffic_note": "dram bytes read + written by ONE launch (round 10 of a 65,536-problem solve) from the "
+                          "traffic_note": "dram bytes read + written by the kernel over 65,536 problems (round 10 of a solve) from the "
                                           "committed ncu --set full capture; the state lives in HBM between stage kernels",
                           "launches_per_step": int(n_qp), "avg_launch_ms": ms_qp / max(n_qp, 1.0),
                           "share_of_step": ms_qp / (ms_ls + ms_qp), "line_search_kernel_ms": ms_ls, "qp_kernel_ms": ms_qp,
