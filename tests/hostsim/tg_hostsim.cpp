@@ -81,3 +81,14 @@ extern "C" void hs_fd_derivatives(const int *spec, const double *par, const doub
     }
 }
 #endif
+
+#ifdef TG_WITH_SQP
+// the BFGS factor update on its own: L D L' <- L D L' + sigma z z'.  Lm: n x n, unit lower factor stored as the solver
+// stores it (column i at Lm[i*n + j], j > i); Dd: n.  Both are updated in place.
+extern "C" void hs_ldl_update(int n, double sigma, const double *z, double *Lm, double *Dd)
+{
+    std::vector<double> zz(z, z + n), w(n + 1), sc(5 * (size_t)n + 5);
+    tg_ldl_update(n, sigma, zz.data(), Lm, Dd, w.data(), sc.data());
+}
+#endif
+

@@ -124,3 +124,56 @@ def test_fd_mode_derivatives_match_scipy_forward_differences(native_lib, hostsim
     e = np.where(np.isfinite(e), e, 0.0)
     assert e.max() <= 2e-6, (name, e.max(), np.unravel_index(e.argmax(), e.shape))
     assert np.abs(g - gref).max() <= 2e-6 * max(1.0, np.abs(gref).max())
+
+
+def _ldl_dense(Lm, Dd, n):
+    """B = L D L' from the solver's storage (unit lower factor, column i at Lm[i*n + j], j > i)."""
+    Lf = np.eye(n)
+    for i in range(n):
+        for j in range(i + 1, n):
+            Lf[j, i] = Lm[i * n + j]
+    return Lf @ np.diag(Dd) @ Lf.T
+
+
+@pytest.mark.parametrize("n", [1, 2, 5, 17, 37])
+def test_factor_update_against_dense_arithmetic(hostsim, n):
+    """tg_ldl_update (three phases: recurrence / scalars of every column at once / columns of L) against
+    B + sigma z z' formed densely, for the two updates of a damped BFGS step (sigma > 0, then sigma < 0 with a
+    positive definite result), and for a large positive update that takes the alpha > 4 branch."""
+    import ctypes
+    ND = np.ctypeslib.ndpointer(dtype=np.float64, flags="C")
+    hostsim.lib.hs_ldl_update.argtypes = [ctypes.c_int, ctypes.c_double, ND, ND, ND]
+    hostsim.lib.hs_ldl_update.restype = None
+    rng = np.random.default_rng(100 + n)
+    for trial in range(20):
+        Lm = np.zeros(n * n)
+        for i in range(n):
+            for j in range(i + 1, n):
+                Lm[i * n + j] = rng.normal() * 0.5
+        Dd = rng.uniform(0.1, 3.0, n)
+        B = _ldl_dense(Lm, Dd, n)
+        s = rng.normal(size=n)
+        u = B @ s + rng.normal(size=n) * 0.3
+        if u @ s < 0.2 * (s @ B @ s):
+            u = u + s * (1.0 + abs(u @ s)) / (s @ s)
+        scale = 50.0 if trial % 4 == 3 else 1.0            # a large update: alpha = t'/t > 4 in some columns
+        steps = [(scale / (u @ s), u.copy()), (-1.0 / (s @ B @ s), (B @ s).copy())]
+        for sigma, z in steps:
+            B = B + sigma * np.outer(z, z)
+            hostsim.lib.hs_ldl_update(n, float(sigma), np.ascontiguousarray(z), Lm, Dd)
+            got = _ldl_dense(Lm, Dd, n)
+            assert np.all(Dd > 0)
+            assert np.abs(got - B).max() <= 1e-10 * max(1.0, np.abs(B).max()), (n, trial, sigma)
+
+
+def test_factor_update_with_zero_weight_is_a_no_op(hostsim):
+    import ctypes
+    ND = np.ctypeslib.ndpointer(dtype=np.float64, flags="C")
+    hostsim.lib.hs_ldl_update.argtypes = [ctypes.c_int, ctypes.c_double, ND, ND, ND]
+    hostsim.lib.hs_ldl_update.restype = None
+    n = 4
+    Lm = np.arange(16, dtype=np.float64) / 10; Dd = np.array([1.0, 2.0, 3.0, 4.0])
+    L0, D0 = Lm.copy(), Dd.copy()
+    hostsim.lib.hs_ldl_update(n, 0.0, np.ones(n), Lm, Dd)
+    assert np.array_equal(Lm, L0) and np.array_equal(Dd, D0)
+
