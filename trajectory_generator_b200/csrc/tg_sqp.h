@@ -299,13 +299,14 @@ TG_HD void tg_qp_normal(const TgSqpWs &W, int nq, int p, double *np)
     TG_SYNC();
 }
 
-// value of constraint p at xq (lane-parallel reduction; same result on all lanes)
+// value of constraint p at xq (lane-parallel reduction; same result on all lanes).  W.np holds the normal of p
+// (tg_qp_normal): row p of A is not read a second time
 TG_HD double tg_qp_value(const TgSqpWs &W, int nq, int p)
 {
     if (p < W.m) {
         double s = 0;
         #pragma unroll 1
-        for (int i = TG_LANE(); i < nq; i += TG_NL) s += W.A[i * W.lda + p] * W.xq[i];
+        for (int i = TG_LANE(); i < nq; i += TG_NL) s += W.np[i] * W.xq[i];
         return tg_wsum(s) + W.c[p];
     }
     const int q = p - W.m;
