@@ -55,3 +55,71 @@ def test_synthetic_generators_match_the_packer(native_lib, name):
         assert np.abs(pp.x0 - b.x0[i]).max() <= 1e-13
     # same seed -> same batch (the CPU baseline regenerates it in its worker processes)
     assert np.array_equal(syn.make(name, 257).par, b.par)
+
+
+def _rows_from_container(d, cc, kw):
+    """Arguments of batched.assemble_rows for ONE container (a batch of two identical rows), read off the
+    dataclasses the way a user of the batched front end would."""
+    import torch
+    wd, db, tb, obs = cc.waypoint_constraints, cc.derivative_constraints, cc.turning_constraint, cc.obstacle_constraints
+    sw, ew = wd.start_waypoint, wd.end_waypoint
+    t = lambda a: None if a is None else torch.from_numpy(np.stack([np.asarray(a, dtype=np.float64).reshape(-1)] * 2))
+    args = dict(start=t(sw.location), end=t(ew.location),
+                start_zero_velocity=sw.checkIfZeroVel(), end_zero_velocity=ew.checkIfZeroVel(),
+                start_velocity=None if sw.checkIfZeroVel() else t(sw.velocity),
+                end_velocity=None if ew.checkIfZeroVel() else t(ew.velocity),
+                end_is_target=bool(ew.is_target), start_direction=t(sw.direction), end_direction=t(ew.direction),
+                start_acceleration=t(sw.acceleration), end_acceleration=t(ew.acceleration),
+                objective_function_type=kw.get("objective_function_type", "minimal_velocity_and_time_path"),
+                num_intervals_free_space=kw.get("num_intervals_free_space"))
+    if wd.intermediate_locations is not None:
+        args["intermediate_locations"] = torch.from_numpy(np.stack([wd.intermediate_locations] * 2))
+        if wd.intermediate_velocities is not None:
+            args["intermediate_velocities"] = torch.from_numpy(np.stack([wd.intermediate_velocities] * 2))
+    if db is not None:
+        args.update(max_velocity=db.max_velocity, max_acceleration=db.max_acceleration, max_jerk=db.max_jerk,
+                    gravity=db.gravity, max_upward_velocity=db.max_upward_velocity,
+                    max_horizontal_velocity=db.max_horizontal_velocity, min_velocity=db.min_velocity)
+        if db.checkIfTangentialAccelerationActive():
+            args["tangential_acceleration"] = (db.min_tangential_acceleration, db.max_tangential_acceleration)
+    if tb is not None and tb.checkIfTurningBoundActive():
+        args["turning"] = (tb.bound_type, tb.max_turning_bound)
+    if obs is not None:
+        ctr = np.array([[float(np.asarray(o.center).flatten()[c]) for c in range(d)] for o in obs])      # [K, d]
+        args["obstacle_centers"] = torch.from_numpy(np.stack([ctr] * 2))
+        args["obstacle_radii"] = torch.from_numpy(np.stack([np.array([float(o.radius) for o in obs])] * 2))
+    return args
+
+
+@pytest.mark.parametrize("name", [n for n in problems.ALL if "sfc" not in n])
+def test_batched_assembly_equals_the_packer(native_lib, name):
+    """The batched front end's descriptor and parameter rows (assembled with torch ops on any device) are those of
+    pack_problem, for every field of a container: directions, accelerations, zero-velocity and target waypoints,
+    every derivative bound, tangential acceleration, all turning kinds, obstacles, intermediate waypoints.
+    (Corridor blocks are filled by a CUDA kernel: tests/test_batched.py, tests/test_build.py.)"""
+    import torch
+    from trajectory_generator_b200.batched import assemble_rows
+    from trajectory_generator_b200.problem import pack_problem
+    d, cc, kw = problems.ALL[name](helpers.product_namespace())
+    pp = pack_problem(d, cc, kw.get("objective_function_type", "minimal_velocity_and_time_path"),
+                      kw.get("num_intervals_free_space"))
+    spec, blocks, i_sfc, ipc = assemble_rows(d, **_rows_from_container(d, cc, kw))
+    assert i_sfc is None and ipc is None
+    assert np.array_equal(spec, pp.spec), (spec, pp.spec)
+    par = torch.cat(blocks, 1).numpy()
+    assert par.shape == (2, pp.layout.P)
+    assert np.array_equal(par[0], pp.par) and np.array_equal(par[1], pp.par)
+
+
+def test_batched_assembly_rejects_what_the_dataclasses_reject(native_lib):
+    import torch
+    from trajectory_generator_b200.batched import assemble_rows
+    z = torch.zeros((2, 2), dtype=torch.float64)
+    with pytest.raises(IndexError):
+        assemble_rows(2, z, z + 1)                                              # location-only terminal waypoint
+    with pytest.raises(Exception, match="Invalid objective function type"):
+        assemble_rows(2, z, z + 1, z + 1, z + 1, objective_function_type="fastest_path")
+    with pytest.raises(Exception, match="general max velocity"):
+        assemble_rows(2, z, z + 1, z + 1, z + 1, max_upward_velocity=1.0)
+    with pytest.raises(Exception, match="non-zero velocity"):
+        assemble_rows(2, z, z + 1, z + 1, z + 1, start_direction=z + 1)
