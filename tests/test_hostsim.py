@@ -177,3 +177,26 @@ def test_factor_update_with_zero_weight_is_a_no_op(hostsim):
     hostsim.lib.hs_ldl_update(n, 0.0, np.ones(n), Lm, Dd)
     assert np.array_equal(Lm, L0) and np.array_equal(Dd, D0)
 
+
+
+def test_augmented_subproblem_on_infeasible_corridor_problems(native_lib, hostsim):
+    """3-D corridor problems made infeasible (velocity / acceleration bounds far too tight): every iteration
+    solves the slack-variable subproblem, and its violation scan takes the corridor rows through the hull points
+    with the slack column on top.  The iterates follow scipy's compiled SLSQP core."""
+    from trajectory_generator_b200 import synthetic as syn
+    from trajectory_generator_b200.problem import pack_problem
+    b = syn.make("C4", 8)
+    L = b.layout
+    for i in range(3):
+        d, cc, kw = syn.container_for(b, i)
+        pp = pack_problem(d, cc, kw.get("objective_function_type", syn.OBJECTIVE["C4"]), kw.get("num_intervals_free_space"))
+        pp.par = pp.par.copy()
+        pp.par[L.p_maxv] = 0.05
+        pp.par[L.p_maxa] = 1e-4
+        rec = []
+        ref = hostsim_loader.scipy_core_solve(hostsim, pp, maxiter=12, record=rec)
+        mine = hostsim.solve(pp, maxiter=12, trace=True)
+        assert (mine["status"], mine["nit"]) == (ref["status"], ref["nit"]) == (9, 12)
+        assert len(rec) >= 10
+        for it, fx, xk in rec[:10]:
+            assert np.abs(mine["trace"][it - 1][2:] - xk).max() <= 1e-8, (i, it)
