@@ -98,15 +98,30 @@ def initial_intermediate_times(waypoint_locations, num_cont_pts):
     return (cum / cum[nseg - 1])[:-1] * (num_cont_pts - 3)
 
 
+PATH_OBJECTIVES = ("minimal_distance_path", "minimal_velocity_path", "minimal_acceleration_path")
+
+
 def pack_problem(dimension, constraints_container, objective_function_type="minimal_velocity_and_time_path",
-                 num_intervals_free_space_arg=None, initial_control_points_arg=None, initial_scale_factor=None):
+                 num_intervals_free_space_arg=None, initial_control_points_arg=None, initial_scale_factor=None,
+                 path_mode=None):
+    """path_mode None: the problem TrajectoryGenerator.generate_trajectory hands to SLSQP
+    (TG/trajectory_generator.py:65-97, 171-250).  path_mode "direct" / "indirect": the problem
+    PathGenerator.generate_path builds (TG/path_generator.py:45-82, 145-202): plain location rows at both ends
+    whatever the velocities, direction rows only (always the s (P2 - P0) / 2 form), intermediate locations
+    without velocities, the curvature bound as the turning row ("direct") or as min velocity 0.5 / max
+    acceleration kappa 0.5^2 ("indirect", :177-185), corridors, obstacles; no derivative bounds of the container."""
     d = int(dimension)
     cc = constraints_container
     wd, db, tb = cc.waypoint_constraints, cc.derivative_constraints, cc.turning_constraint
     sfc, obstacles = cc.sfc_constraints, cc.obstacle_constraints
     sw, ew = wd.start_waypoint, wd.end_waypoint
-    if objective_function_type not in OBJECTIVES:
+    if path_mode not in (None, "direct", "indirect"):
+        raise ValueError("path_mode must be None, 'direct' or 'indirect'")
+    if objective_function_type not in (OBJECTIVES if path_mode is None else PATH_OBJECTIVES):
         raise Exception("Error, Invalid objective function type")
+    if path_mode is not None:
+        return _pack_path_problem(d, cc, objective_function_type, num_intervals_free_space_arg,
+                                  initial_control_points_arg, initial_scale_factor, path_mode == "indirect")
 
     # ---- sizes (TG/trajectory_generator.py:134-162)
     mew0 = num_intervals_free_space(wd, num_intervals_free_space_arg)
@@ -176,35 +191,24 @@ def pack_problem(dimension, constraints_container, objective_function_type="mini
         spec[SP_TURN] = TURN_KINDS[tb.bound_type]
         par.append(np.array([float(tb.max_turning_bound)]))
 
-    # ---- safe flight corridors (CF/sfc_constraints.py:7-77)
+    # ---- safe flight corridors, obstacles
     if sfc is not None:
-        ipc = sfc.get_intervals_per_corridor()
-        ipc = [int(ipc)] if np.ndim(ipc) == 0 else [int(v) for v in ipc]
-        if len(ipc) > MAX_CORRIDORS:
-            raise Exception("at most %d corridors are supported" % MAX_CORRIDORS)
-        if sum(ipc) != nint:
-            raise Exception("intervals per corridor do not add up to the number of intervals")
-        spec[SP_NCORR] = len(ipc)
-        spec[SP_IPC0:SP_IPC0 + len(ipc)] = ipc
-        for box in sfc.get_sfc_list()[:len(ipc)]:
-            lo, hi = box.getRotatedBounds()
-            par += [_flat(np.asarray(box.rotation).T), _flat(lo), _flat(hi)]
-
-    # ---- obstacles (CF/obstacle_constraints.py:93-113)
+        par += _corridor_blocks(spec, sfc, nint)
     if obstacles is not None:
-        K = len(obstacles)
-        spec[SP_NOBST] = K
-        centers = np.array([[float(np.asarray(o.center).flatten()[c]) for o in obstacles] for c in range(d)])
-        par += [centers.flatten(), np.array([float(o.radius) for o in obstacles])]
+        par += _obstacle_blocks(spec, obstacles, d)
 
+    return _finish_packing(d, N, spec, par, wd, sfc, initial_control_points_arg, initial_scale_factor)
+
+
+def _finish_packing(d, N, spec, par, wd, sfc, initial_control_points_arg, initial_scale_factor):
+    """parameter row, initial variables and bounds (TG/objectives/objective_variables.py:27-61)"""
+    niw = wd.get_num_intermediate_waypoints()
     par = np.concatenate(par) if par else np.zeros(0)
     packed = PackedProblem(spec, None, None, None, None)
     lay = packed.layout
     if lay.P != par.size:
         raise RuntimeError("parameter row has %d entries, layout expects %d" % (par.size, lay.P))
     n = lay.n
-
-    # ---- variables (TG/objectives/objective_variables.py:27-61)
     seq = wd.get_waypoint_locations() if sfc is None else sfc.get_point_sequence()
     if initial_control_points_arg is not None:
         cps = np.asarray(initial_control_points_arg, dtype=np.float64)
@@ -224,3 +228,76 @@ def pack_problem(dimension, constraints_container, objective_function_type="mini
         xu[lay.it0:] = N - 3
     packed.par, packed.x0, packed.xl, packed.xu = np.ascontiguousarray(par, dtype=np.float64), x0, xl, xu
     return packed
+
+
+def _corridor_blocks(spec, sfc, nint):
+    """descriptor entries and parameter blocks of the corridors (CF/sfc_constraints.py:7-77)"""
+    ipc = sfc.get_intervals_per_corridor()
+    ipc = [int(ipc)] if np.ndim(ipc) == 0 else [int(v) for v in ipc]
+    if len(ipc) > MAX_CORRIDORS:
+        raise Exception("at most %d corridors are supported" % MAX_CORRIDORS)
+    if sum(ipc) != nint:
+        raise Exception("intervals per corridor do not add up to the number of intervals")
+    spec[SP_NCORR] = len(ipc)
+    spec[SP_IPC0:SP_IPC0 + len(ipc)] = ipc
+    par = []
+    for box in sfc.get_sfc_list()[:len(ipc)]:
+        lo, hi = box.getRotatedBounds()
+        par += [_flat(np.asarray(box.rotation).T), _flat(lo), _flat(hi)]
+    return par
+
+
+def _obstacle_blocks(spec, obstacles, d):
+    """CF/obstacle_constraints.py:93-113"""
+    spec[SP_NOBST] = len(obstacles)
+    centers = np.array([[float(np.asarray(o.center).flatten()[c]) for o in obstacles] for c in range(d)])
+    return [centers.flatten(), np.array([float(o.radius) for o in obstacles])]
+
+
+def _pack_path_problem(d, cc, objective_function_type, num_intervals_free_space_arg, initial_control_points_arg,
+                       initial_scale_factor, indirect):
+    wd, tb, sfc, obstacles = cc.waypoint_constraints, cc.turning_constraint, cc.sfc_constraints, cc.obstacle_constraints
+    sw, ew = wd.start_waypoint, wd.end_waypoint
+    # ---- sizes (TG/path_generator.py:104-135: the same rule as the trajectory generator's)
+    mew0 = num_intervals_free_space(wd, num_intervals_free_space_arg)
+    if initial_control_points_arg is not None:
+        nint = np.shape(initial_control_points_arg)[1] - 3
+    elif sfc is not None:
+        nint = sfc.get_num_intervals()
+    else:
+        nint = mew0
+    N = int(nint + 3)
+    spec = np.zeros(SP_COUNT, dtype=np.int32)
+    spec[SP_DIM], spec[SP_NCP] = d, N
+    spec[SP_OBJECTIVE] = OBJECTIVES.index(objective_function_type)
+    # ---- plain location rows at both ends (:148-155), direction rows (:156-165)
+    par = [_flat(sw.location), _flat(ew.location)]
+    for wp, f_dir in ((sw, SP_START_DIR), (ew, SP_END_DIR)):
+        if wp.checkIfDirectionActive():
+            if indirect:
+                # the reference's indirect direction row divides by the waypoint scalar at the start and cancels it
+                # at the end (CF/waypoint_constraints.py:212-217): not one of the row kinds of this library
+                raise Exception("isIndirect with a waypoint direction is not supported")
+            spec[f_dir] = 1
+            par.append(_flat(wp.direction))
+    # ---- intermediate locations (:166-170; velocities of intermediate waypoints are not read)
+    niw = wd.get_num_intermediate_waypoints()
+    spec[SP_NIW] = niw
+    if niw:
+        par.append(_flat(wd.intermediate_locations))
+    # ---- curvature bound (:174-190)
+    if tb is not None and tb.checkIfCurvatureBoundActive():
+        if indirect:
+            min_velocity = 0.5
+            spec[SP_DB_MINV] = 1
+            par.append(np.array([min_velocity]))
+            spec[SP_DB_MAXA] = 1
+            par.append(np.array([float(tb.max_turning_bound) * min_velocity ** 2]))
+        else:
+            spec[SP_TURN] = TURN_KINDS["curvature"]
+            par.append(np.array([float(tb.max_turning_bound)]))
+    if sfc is not None:
+        par += _corridor_blocks(spec, sfc, nint)
+    if obstacles is not None:
+        par += _obstacle_blocks(spec, obstacles, d)
+    return _finish_packing(d, N, spec, par, wd, sfc, initial_control_points_arg, initial_scale_factor)
