@@ -123,3 +123,79 @@ def test_batched_assembly_rejects_what_the_dataclasses_reject(native_lib):
         assemble_rows(2, z, z + 1, z + 1, z + 1, max_upward_velocity=1.0)
     with pytest.raises(Exception, match="non-zero velocity"):
         assemble_rows(2, z, z + 1, z + 1, z + 1, start_direction=z + 1)
+
+
+def test_batched_assembly_equals_the_packer_on_random_containers(native_lib):
+    """Random combinations of every container field (seeded): assemble_rows == pack_problem, descriptor and row."""
+    import torch
+    from trajectory_generator_b200.batched import assemble_rows
+    from trajectory_generator_b200.problem import pack_problem
+    ns = helpers.product_namespace()
+    W, WD, DB, TB, Ob, CC = (ns[k] for k in ("Waypoint", "WaypointData", "DerivativeBounds", "TurningBound", "Obstacle",
+                                               "ConstraintsContainer"))
+    rng = np.random.default_rng(20261018)
+    objectives = ["minimal_time_path", "minimal_distance_path", "minimal_velocity_path", "minimal_acceleration_path",
+                  "minimal_distance_and_time_path", "minimal_velocity_and_time_path", "minimal_acceleration_and_time_path",
+                  "minimal_time_path_velocity_penalty"]
+    checked = 0
+    for trial in range(120):
+        d = int(rng.integers(2, 4))
+        vec = lambda: rng.normal(size=(d, 1)) * 3
+
+        def terminal(is_end):
+            kind = rng.integers(0, 5)
+            kwargs = dict(location=vec())
+            if kind == 0:
+                kwargs["velocity"] = vec()
+            elif kind == 1:
+                kwargs["velocity"] = np.zeros((d, 1))                       # zero-velocity waypoint
+            elif kind == 2:
+                kwargs["velocity"] = np.zeros((d, 1)); kwargs["direction"] = vec()
+            elif kind == 3:
+                kwargs["direction"] = vec()
+            else:
+                kwargs["velocity"] = vec(); kwargs["acceleration"] = vec()
+            if rng.random() < 0.2 and kind != 0:
+                kwargs["acceleration"] = vec()
+            if is_end and kind in (0, 4) and rng.random() < 0.3:
+                kwargs["is_target"] = True
+            return W(**kwargs)
+        wps = [terminal(False)]
+        niw = int(rng.integers(0, 3))
+        with_iv = rng.random() < 0.5
+        for _ in range(niw):
+            wps.append(W(location=vec(), velocity=vec() if with_iv else None))
+        wps.append(terminal(True))
+        db = None
+        if rng.random() < 0.8:
+            f = {}
+            if rng.random() < 0.7: f["max_velocity"] = float(rng.uniform(3, 9))
+            if rng.random() < 0.5: f["max_acceleration"] = float(rng.uniform(1, 9))
+            if rng.random() < 0.3: f["max_jerk"] = float(rng.uniform(1, 9))
+            if rng.random() < 0.3: f["gravity"] = float(rng.uniform(0.1, 1))
+            if rng.random() < 0.3: f["min_velocity"] = float(rng.uniform(0.01, 0.5))
+            if "max_velocity" in f and rng.random() < 0.4: f["max_upward_velocity"] = f["max_velocity"] * 0.5
+            if "max_velocity" in f and rng.random() < 0.4: f["max_horizontal_velocity"] = f["max_velocity"] * 0.8
+            if rng.random() < 0.3:
+                f["min_tangential_acceleration"] = -float(rng.uniform(1, 5)); f["max_tangential_acceleration"] = float(rng.uniform(1, 5))
+            db = DB(**f)
+        tb = TB(float(rng.uniform(0.5, 5)), ["curvature", "angular_rate", "centripetal_acceleration"][rng.integers(0, 3)]) \
+            if rng.random() < 0.6 else None
+        obs = [Ob(center=vec(), radius=float(rng.uniform(0.2, 1))) for _ in range(int(rng.integers(1, 4)))] \
+            if rng.random() < 0.5 else None
+        cc = CC(WD(tuple(wps)), db, tb, None, obs)
+        kw = dict(objective_function_type=objectives[rng.integers(0, len(objectives))])
+        if rng.random() < 0.5:
+            kw["num_intervals_free_space"] = int(rng.integers(4, 12))
+        try:
+            pp = pack_problem(d, cc, kw["objective_function_type"], kw.get("num_intervals_free_space"))
+        except IndexError:
+            with pytest.raises(IndexError):         # a terminal waypoint without any derivative row: both refuse
+                assemble_rows(d, **_rows_from_container(d, cc, kw))
+            continue
+        spec, blocks, i_sfc, ipc = assemble_rows(d, **_rows_from_container(d, cc, kw))
+        assert np.array_equal(spec, pp.spec), (trial, spec, pp.spec)
+        par = torch.cat(blocks, 1).numpy()
+        assert par.shape == (2, pp.layout.P) and np.array_equal(par[0], pp.par), trial
+        checked += 1
+    assert checked >= 80
