@@ -199,3 +199,52 @@ def test_batched_assembly_equals_the_packer_on_random_containers(native_lib):
         assert par.shape == (2, pp.layout.P) and np.array_equal(par[0], pp.par), trial
         checked += 1
     assert checked >= 80
+
+
+def test_batched_problem_constructor_plumbing(native_lib, monkeypatch):
+    """BatchedProblem's constructor end to end on the CPU with the two CUDA builders stubbed out (tensors that claim
+    to be CUDA tensors): descriptor, parameter rows, the arguments handed to the builders.  The builders themselves
+    and the solve are covered on the GPU (tests/test_batched.py, tests/test_build.py)."""
+    import torch
+    from trajectory_generator_b200 import batched, builder, synthetic as syn
+
+    class Claimed(torch.Tensor):
+        @property
+        def is_cuda(self):
+            return True
+
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).as_subclass(Claimed)
+    calls = {}
+
+    def fake_guess(spec, seq, wseq, scale):
+        calls["guess"] = (np.array(spec), tuple(seq.shape), None if wseq is None else tuple(wseq.shape), scale)
+        return torch.zeros((seq.shape[0], batched.pk.Layout(spec).n), dtype=torch.float64)
+
+    def fake_boxes(spec, points, pads, par):
+        calls["boxes"] = (tuple(points.shape), tuple(pads.shape), tuple(par.shape))
+
+    monkeypatch.setattr(builder, "initial_guess_batch", fake_guess)
+    monkeypatch.setattr(builder, "sfc_boxes_batch", fake_boxes)
+    # C2: obstacles; C3: intermediate waypoints; C4: corridors (as tests/test_batched.py builds them)
+    b = syn.make("C2", 8); r = b.raw
+    bp = batched.BatchedProblem(2, t(r["start"]), t(r["goal"]), t(r["v0"]), t(r["v1"]), max_velocity=r["vmax"],
+                                max_acceleration=r["amax"], turning=("angular_rate", r["turn"]),
+                                obstacle_centers=t(r["centers"]), obstacle_radii=t(r["radii"]))
+    assert np.array_equal(bp.spec, b.spec) and np.array_equal(bp.par.numpy(), b.par)
+    assert calls["guess"][1:] == ((8, 2, 2), None, 1.0) and (bp.B, bp.d, bp.N) == (8, 2, b.layout.N)
+    b = syn.make("C3", 8); p, v = b.raw["points"], b.raw["velocities"]
+    bp = batched.BatchedProblem(2, t(p[:, :, 0]), t(p[:, :, 3]), t(v[:, :, 0]), t(v[:, :, 3]),
+                                intermediate_locations=t(p[:, :, 1:3]), intermediate_velocities=t(v[:, :, 1:3]),
+                                max_velocity=b.raw["vmax"], turning=("curvature", b.raw["turn"]), num_intervals_free_space=14)
+    assert np.array_equal(bp.spec, b.spec) and np.array_equal(bp.par.numpy(), b.par)
+    assert calls["guess"][1:3] == ((8, 2, 4), (8, 2, 4))
+    b = syn.make("C4", 8); p = b.raw["points"]
+    pad = b.raw["dims"].copy(); pad[:, :, 0] -= np.linalg.norm(p[:, :, 1:] - p[:, :, :-1], 2, 1)
+    bp = batched.BatchedProblem(3, t(p[:, :, 0]), t(p[:, :, 4]), t(b.raw["v0"]), end_zero_velocity=True,
+                                max_velocity=b.raw["vmax"], max_acceleration=b.raw["amax"], corridor_points=t(p),
+                                corridor_pads=t(pad), objective_function_type="minimal_velocity_path")
+    assert np.array_equal(bp.spec, b.spec) and bp.par.shape == b.par.shape
+    assert calls["boxes"] == ((8, 3, 5), (8, 4, 3), (8, b.layout.P)) and calls["guess"][1:3] == ((8, 3, 5), None)
+    # a field of the extended set goes through the constructor's keyword pass-through
+    bp = batched.BatchedProblem(2, t(r["start"]), t(r["goal"]), None, t(r["v1"]), start_direction=t(r["v0"]), max_jerk=3.0)
+    assert bp.spec[batched.pk.SP_START_DIR] == 1 and bp.spec[batched.pk.SP_DB_JERK] == 1 and bp.layout.nws == 1
