@@ -1,0 +1,25 @@
+#!/bin/bash
+# AddressSanitizer run of the single-lane host build of the kernel source (tests/hostsim) over every fixture shape
+# (trajectory and path mode): the host buffers are sized by the same tg_sqp_workspace_doubles / tg_scratch_doubles
+# the CUDA library uses, so an out-of-bounds index of tg_eval.h / tg_sqp.h shows up here.  CPU only.
+set -e
+cd "$(dirname "$0")/.."
+g++ -std=c++14 -O1 -g -fPIC -shared -fsanitize=address -fno-omit-frame-pointer -ffp-contract=off -Wno-unknown-pragmas \
+    -DTG_WITH_SQP -o /tmp/asan_hostsim.so tests/hostsim/tg_hostsim.cpp
+LD_PRELOAD=$(g++ -print-file-name=libasan.so) ASAN_OPTIONS=detect_leaks=0 python - <<'PY'
+import sys
+sys.path[:0] = [".", "tests", "oracle"]
+import helpers, path_problems, problems, hostsim_loader
+from trajectory_generator_b200.problem import pack_problem
+hs = hostsim_loader.HostSim("/tmp/asan_hostsim.so")
+ns = helpers.product_namespace()
+for table, default, mode in ((path_problems.ALL, "minimal_velocity_path", True), (problems.ALL, "minimal_velocity_and_time_path", False)):
+    for name, make in table.items():
+        d, cc, kw = make(ns)
+        pm = ("indirect" if kw.get("isIndirect") else "direct") if mode else None
+        pp = pack_problem(d, cc, kw.get("objective_function_type", default), kw.get("num_intervals_free_space"), path_mode=pm)
+        for fd in (True, False):
+            r = hs.solve(pp, fd=fd, maxiter=40)
+        hs.eval(pp, pp.x0)
+        print("%-5s %-28s clean (status %d, %d iterations)" % ("path" if mode else "traj", name, r["status"], r["nit"]))
+PY
