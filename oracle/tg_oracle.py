@@ -658,6 +658,18 @@ class OracleProblem:
         err = np.where(np.isfinite(err), err, np.where(trusted, np.inf, 0.0))
         return err, trusted
 
+    # ---- TG/trajectory_generator.py:252-275, DS/constraint_function_data.py:12,45-48 ----
+    def is_violation(self, x, success=False):
+        """The reference's third return value: False after a successful solve; otherwise the loop over the
+        constraint list overwrites the flag every time, so only the LAST constraint decides -- any output of it
+        outside [lb - 10e-6, ub + 10e-6]."""
+        if success or not self.blocks:
+            return False
+        b = self.blocks[-1]
+        y = np.atleast_1d(np.array(b.fun(np.asarray(x, dtype=float)), dtype=float)).flatten()
+        with np.errstate(all="ignore"):
+            return bool(np.any((y > np.asarray(b.ub, dtype=float) + 10e-6) | (y < np.asarray(b.lb, dtype=float) - 10e-6)))
+
     # ---- TG/trajectory_generator.py:85-97 through scipy ----
     def scipy_constraints(self):
         """The old-style dicts scipy builds from the reference's constraint tuple."""

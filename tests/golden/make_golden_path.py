@@ -23,6 +23,9 @@ import problems  # noqa: E402
 import path_problems  # noqa: E402
 
 
+NEIGHBOUR_ULPS = (1, -1, 2, -2, 3, -3, 4, -4)
+
+
 def main():
     ns = ref_import.namespace()
     import scipy
@@ -70,6 +73,15 @@ def main():
 
             def spy(*a, **k):
                 captured["res"] = real_minimize(*a, **k)
+                # the reference against itself from x0 + k ulp (see make_golden.py)
+                x0k = np.asarray(k["x0"], dtype=float)
+                captured["nbr"] = []
+                for ulps in NEIGHBOUR_ULPS:
+                    xk = x0k.copy()
+                    for _ in range(abs(ulps)):
+                        xk = np.nextafter(xk, np.inf if ulps > 0 else -np.inf)
+                    k2 = dict(k); k2["x0"] = xk
+                    captured["nbr"].append(real_minimize(*a, **k2))
                 return captured["res"]
             pgmod.minimize = spy
             try:
@@ -79,9 +91,23 @@ def main():
             res = captured["res"]
             rec["solve"] = dict(x=np.asarray(res.x).tolist(), status=int(res.status), nit=int(res.nit),
                                 fun=float(res.fun), control_points=np.asarray(cp).tolist())
+            ncp = d * int(N) + 1
+
+            def feas(xv):
+                c = cons(np.asarray(xv))
+                return (float(c[meq:].min()) if len(c) > meq else 0.0, float(np.abs(c[:meq]).max()) if meq else 0.0)
+            nb = [dict(ulps=int(u), status=int(r.status), nit=int(r.nit), fun=float(r.fun),
+                       dcp=float(np.abs(np.asarray(r.x)[:ncp] - np.asarray(res.x)[:ncp]).max()),
+                       c_min_ineq=feas(r.x)[0], c_max_eq=feas(r.x)[1]) for u, r in zip(NEIGHBOUR_ULPS, captured["nbr"])]
+            rec["solve"]["neighbours"] = nb
+            rec["solve"]["status_stable"] = bool(all(q["status"] == res.status for q in nb))
+            rec["solve"]["stable"] = bool(rec["solve"]["status_stable"] and res.status == 0
+                                          and all(q["dcp"] <= 1e-5 for q in nb))
+            rec["solve"]["c_min_ineq"], rec["solve"]["c_max_eq"] = feas(res.x)
         out["problems"][name] = rec
-        print("%-28s n=%2d meq=%2d m=%3d status=%d nit=%d" % (name, rec["n"], rec["meq"], rec["m"],
-                                                             rec["solve"]["status"], rec["solve"]["nit"]))
+        print("%-28s n=%2d meq=%2d m=%3d status=%d nit=%d stable=%s nbr dcp %.1e nit %d..%d" % (
+            name, rec["n"], rec["meq"], rec["m"], rec["solve"]["status"], rec["solve"]["nit"], rec["solve"]["stable"],
+            max(q["dcp"] for q in nb), min(q["nit"] for q in nb), max(q["nit"] for q in nb)))
 
     def enc(o):
         if isinstance(o, float):

@@ -72,20 +72,19 @@ def test_sqp_augmented_subproblem_path(native_lib, hostsim):
     assert np.abs(mine["x"] - ref["x"]).max() <= 1e-4
 
 
-@pytest.mark.parametrize("name", ["c1_sfc2d", "obstacle2d", "sfc3d", "sfc3d_four"])
+@pytest.mark.parametrize("name", list(problems.SOLVE))
 def test_fd_mode_reproduces_reference_solves(native_lib, hostsim, name):
-    """Finite-difference emulation: converged control points within 1e-5 of the reference's own solve
-    (fixture recorded by running the unmodified reference), identical status flag."""
-    pp, _ = _problem(name)
+    """Finite-difference emulation against EVERY recorded solve of the unmodified reference, under the contract of
+    tests/parity_contract.py (read off the reference's own reproducibility runs stored in the fixture)."""
+    import parity_contract
+    pp, op = _problem(name)
     s = helpers.load_golden()["problems"][name]["solve"]
     mine = hostsim.solve(pp, fd=True)
-    k = pp.layout.ia + 1
-    assert mine["status"] == s["status"] == 0
-    assert np.abs(mine["x"][:k] - np.array(s["x"])[:k]).max() <= 1e-5
+    parity_contract.check(name, s, pp.layout.ia + 1, mine["x"], mine["status"], mine["nit"], mine["f"], op.cons, op.meq)
 
 
 @pytest.mark.parametrize("name", ["c1_curvature", "intermediate_waypoints", "unicycle2"])
-def test_iteration_limit_flag_matches_reference(native_lib, hostsim, name):
+def test_iteration_limit_flag_matches_reference_analytic_mode(native_lib, hostsim, name):
     s = helpers.load_golden()["problems"][name]["solve"]
     mine = hostsim.solve(pp := _problem(name)[0])
     assert (mine["status"], mine["nit"]) == (s["status"], s["nit"]) == (9, 100)

@@ -49,7 +49,12 @@ static int tg_make_shape(const int *spec, TgShape *S)
     return 0;
 }
 
-static int g_sm_count = 0, g_smem_optin = 0;
+// Everything that lives on a device (properties, cached staging buffers, streams) is kept per device id: a
+// process may switch devices between calls (cudaSetDevice) and must never be handed another device's pointers.
+#define TG_MAX_DEVICES 64
+static thread_local int g_sm_count = 0, g_smem_optin = 0;      // of the calling thread's current device (tg_device_check)
+static int g_dev_sm[TG_MAX_DEVICES], g_dev_smem[TG_MAX_DEVICES];
+static std::atomic<int> g_dev_known[TG_MAX_DEVICES];
 template <int D>
 __global__ void tg_legacy_kernel(int what, const double *pts, int N, double alpha, int kind, const double *centers,
                                  const double *radii, int K, double *out);
@@ -61,11 +66,19 @@ extern "C" int tg_device_check(void)
     if (e != cudaSuccess || ndev == 0) return tg_fail(10, "no CUDA device available (this library has no CPU path)", e);
     int dev = 0;
     TG_CUDA(cudaGetDevice(&dev));
-    cudaFuncAttributes attr;
-    e = cudaFuncGetAttributes(&attr, tg_legacy_kernel<2>);
-    if (e != cudaSuccess) return tg_fail(11, "no kernel image for this device (built for sm_100a)", e);
-    TG_CUDA(cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev));
-    TG_CUDA(cudaDeviceGetAttribute(&g_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    if (dev < 0 || dev >= TG_MAX_DEVICES) return tg_fail(10, "device index out of range");
+    if (!g_dev_known[dev].load(std::memory_order_acquire)) {
+        cudaFuncAttributes attr;
+        e = cudaFuncGetAttributes(&attr, tg_legacy_kernel<2>);
+        if (e != cudaSuccess) return tg_fail(11, "no kernel image for this device (built for sm_100a)", e);
+        int sm = 0, smem = 0;
+        TG_CUDA(cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, dev));
+        TG_CUDA(cudaDeviceGetAttribute(&smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+        g_dev_sm[dev] = sm; g_dev_smem[dev] = smem;
+        g_dev_known[dev].store(1, std::memory_order_release);
+    }
+    g_sm_count = g_dev_sm[dev];
+    g_smem_optin = g_dev_smem[dev];
     return 0;
 }
 
@@ -279,7 +292,32 @@ struct TgSliceStreams {
         return cudaSuccess;
     }
 };
-static thread_local TgSliceStreams g_slices;
+// pool of stream sets per device: a solve borrows one for its duration (worker threads of tg_solve_mixed_host come
+// and go, so nothing is tied to a thread and nothing leaks)
+static std::mutex g_slice_mutex;
+static std::vector<TgSliceStreams *> g_slice_free[TG_MAX_DEVICES];
+struct TgSliceLease {
+    TgSliceStreams *s = nullptr;
+    int dev = 0;
+    cudaError_t acquire()
+    {
+        if (s) return cudaSuccess;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e != cudaSuccess) return e;
+        {
+            std::lock_guard<std::mutex> lock(g_slice_mutex);
+            if (!g_slice_free[dev].empty()) { s = g_slice_free[dev].back(); g_slice_free[dev].pop_back(); }
+        }
+        if (!s) s = new TgSliceStreams();
+        return s->init();
+    }
+    ~TgSliceLease()
+    {
+        if (!s) return;
+        std::lock_guard<std::mutex> lock(g_slice_mutex);
+        g_slice_free[dev].push_back(s);
+    }
+};
 
 static int tg_solve_phased(const TgShape &S, const TgSolvePlan &P, int B, const double *par, double *x, double *f,
                            int *status, int *nit, int *violation, int maxiter, double ftol, int flags, void *workspace,
@@ -306,13 +344,15 @@ static int tg_solve_phased(const TgShape &S, const TgSolvePlan &P, int B, const 
     if (const char *v = getenv("TG_SLICES")) want = atoi(v);
     if (want < 1) want = 1;
     if (want > TG_MAX_SLICES) want = TG_MAX_SLICES;
+    TgSliceLease lease;
     for (int lo = 0; lo < B; lo += P.chunk) {
         const int nbc = B - lo < P.chunk ? B - lo : P.chunk;
         const int ns = (timing || nbc < 8192) ? 1 : want;
         if (ns > 1) {
-            TG_CUDA(g_slices.init());
-            TG_CUDA(cudaEventRecord(g_slices.fork, st));
+            TG_CUDA(lease.acquire());
+            TG_CUDA(cudaEventRecord(lease.s->fork, st));
         }
+        TgSliceStreams *const ss = lease.s;          // only touched when ns > 1
         struct Slice { int lo, nb, done; TgRoundCtl *rc; int *lists[2]; double *pws; cudaStream_t st; } sl[TG_MAX_SLICES];
         for (int k = 0; k < ns; k++) {
             Slice &q = sl[k];
@@ -323,8 +363,8 @@ static int tg_solve_phased(const TgShape &S, const TgSolvePlan &P, int B, const 
             q.lists[0] = list_base + q.lo;
             q.lists[1] = list_base + P.chunk + q.lo;
             q.pws = pws_base + (size_t)q.lo * P.np;
-            q.st = ns > 1 ? g_slices.st[k] : st;
-            if (ns > 1) TG_CUDA(cudaStreamWaitEvent(q.st, g_slices.fork, 0));
+            q.st = ns > 1 ? ss->st[k] : st;
+            if (ns > 1) TG_CUDA(cudaStreamWaitEvent(q.st, ss->fork, 0));
             TG_CUDA(cudaMemsetAsync(q.rc, 0, TG_ROUNDCTL_BYTES, q.st));
             TG_LAUNCH(tg_launch_begin_g32(S, q.nb, x + (size_t)(lo + q.lo) * L.n, q.pws, P.np, maxiter, ftol, flags, q.rc,
                                           q.lists[0], q.st), "tg_sqp_begin_kernel");
@@ -372,8 +412,8 @@ static int tg_solve_phased(const TgShape &S, const TgSolvePlan &P, int B, const 
                                            nit ? nit + o : nullptr, violation ? violation + o : nullptr, q.rc, q.st),
                       "tg_sqp_finish_kernel");
             if (ns > 1) {
-                TG_CUDA(cudaEventRecord(g_slices.join[k], q.st));
-                TG_CUDA(cudaStreamWaitEvent(st, g_slices.join[k], 0));
+                TG_CUDA(cudaEventRecord(ss->join[k], q.st));
+                TG_CUDA(cudaStreamWaitEvent(st, ss->join[k], 0));
             }
         }
         if (timing) {
@@ -489,8 +529,19 @@ struct DevBuf {
         return 0;
     }
 };
-static std::mutex g_host_mutex;
-static DevBuf g_par, g_x, g_f, g_g, g_c, g_j, g_i, g_ws;
+// cached device buffers of the host-buffer entry points, one set per device (callers on different devices do not
+// serialise against each other; callers on the same device do)
+struct TgHostCtx {
+    std::mutex mu;
+    DevBuf par, x, f, g, c, j, i, ws;
+};
+static TgHostCtx g_host[TG_MAX_DEVICES];
+static TgHostCtx *tg_host_ctx()
+{
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= TG_MAX_DEVICES) return nullptr;
+    return &g_host[dev];
+}
 
 extern "C" int tg_eval_host(const int *spec, int B, const double *par, const double *x, double *f, double *g, double *c,
                             double *jnl)
@@ -500,7 +551,10 @@ extern "C" int tg_eval_host(const int *spec, int B, const double *par, const dou
     if (rc) return rc;
     if (B <= 0) return 0;
     if ((rc = tg_device_check())) return rc;
-    std::lock_guard<std::mutex> lock(g_host_mutex);
+    TgHostCtx *H = tg_host_ctx();
+    if (!H) return tg_fail(10, "cannot identify the current device");
+    std::lock_guard<std::mutex> lock(H->mu);
+    DevBuf &g_par = H->par, &g_x = H->x, &g_f = H->f, &g_g = H->g, &g_c = H->c, &g_j = H->j;
     const TgLayout &L = S.L;
     const size_t nb = sizeof(double);
     if ((rc = g_par.ensure((size_t)B * (L.P + 1) * nb)) || (rc = g_x.ensure((size_t)B * L.n * nb))) return rc;
@@ -529,7 +583,10 @@ extern "C" int tg_solve_host(const int *spec, int B, const double *par, double *
     if (rc) return rc;
     if (B <= 0) return 0;
     if ((rc = tg_device_check())) return rc;
-    std::lock_guard<std::mutex> lock(g_host_mutex);
+    TgHostCtx *H = tg_host_ctx();
+    if (!H) return tg_fail(10, "cannot identify the current device");
+    std::lock_guard<std::mutex> lock(H->mu);
+    DevBuf &g_par = H->par, &g_x = H->x, &g_f = H->f, &g_i = H->i, &g_ws = H->ws;
     const TgLayout &L = S.L;
     const size_t nb = sizeof(double);
     const size_t wsb = tg_solve_workspace_bytes(spec, B);
@@ -565,8 +622,11 @@ struct TgMixedSlot {
     cudaStream_t st = nullptr;
     DevBuf par, x, f, i, ws;
 };
-static std::mutex g_mixed_mutex;
-static TgMixedSlot g_mixed[TG_MIXED_WORKERS];
+struct TgMixedCtx {
+    std::mutex mu;
+    TgMixedSlot slot[TG_MIXED_WORKERS];
+};
+static TgMixedCtx g_mixed_ctx[TG_MAX_DEVICES];
 
 extern "C" int tg_solve_mixed_host(int nbuckets, const int *specs, const int *counts, const double *const *par,
                                    double *const *x, double *const *f, int *const *status, int *const *nit,
@@ -578,7 +638,9 @@ extern "C" int tg_solve_mixed_host(int nbuckets, const int *specs, const int *co
     if (rc) return rc;
     int dev = 0;
     TG_CUDA(cudaGetDevice(&dev));
-    std::lock_guard<std::mutex> lock(g_mixed_mutex);
+    if (dev < 0 || dev >= TG_MAX_DEVICES) return tg_fail(10, "device index out of range");
+    std::lock_guard<std::mutex> lock(g_mixed_ctx[dev].mu);
+    TgMixedSlot *const g_mixed = g_mixed_ctx[dev].slot;
     // validate every bucket before any work is queued
     for (int k = 0; k < nbuckets; k++) {
         TgShape S;
@@ -762,12 +824,19 @@ __global__ void tg_legacy_kernel(int what, const double *pts, int N, double alph
     }
 }
 
+// Result arrays: the reference returns a fresh `new double[]` from every array-returning call and never frees it
+// (CC/src/ObstacleConstraints.cpp; its ctypes wrappers view it zero-copy through an ndpointer restype,
+// CF/obstacle_constraints.py:53-79).  Here every call also gets a buffer of its own, so an array returned earlier is
+// not overwritten by the next call; instead of leaking all of them, a handle keeps the last TG_LEGACY_RING buffers
+// alive and frees the oldest (documented in INTEGRATION.md section 2).
+#define TG_LEGACY_RING 64
 struct LegacyHandle {
     int D;
     std::mutex mu;
     DevBuf din, dout;
-    double *host_out = nullptr;
-    size_t host_cap = 0;
+    int dev = -1;
+    double *ring[TG_LEGACY_RING] = {nullptr};
+    unsigned long long calls = 0;
 };
 
 static void *tg_new_handle(int D)
@@ -784,19 +853,19 @@ static double *tg_legacy_run(void *obj, int D, int what, const double *pts, int 
     static LegacyHandle fallback[2];
     LegacyHandle *h = obj ? (LegacyHandle *)obj : &fallback[D - 2];
     std::lock_guard<std::mutex> lock(h->mu);
-    if ((size_t)nout + 1 > h->host_cap) {
-        // the previous buffer is intentionally not freed: the reference hands out a fresh
-        // `new double[]` per call and its callers may still hold the old view
-        h->host_cap = (size_t)nout + 64;
-        h->host_out = new double[h->host_cap];
-    }
-    double *res = h->host_out;
+    double *&slot = h->ring[h->calls++ % TG_LEGACY_RING];
+    delete[] slot;
+    slot = new double[(size_t)nout + 1];
+    double *res = slot;
     for (int i = 0; i < nout; i++) res[i] = NAN;
     if (tg_device_check()) { fprintf(stderr, "libTrajectoryConstraints (B200): %s\n", g_err); return res; }
     if (N < 4 && what != LG_BEZ) { fprintf(stderr, "libTrajectoryConstraints (B200): need at least 4 control points\n"); return res; }
     const int nc = (what == LG_INTERVALS) ? D : D * K;
     const int nr = (what == LG_INTERVALS) ? 1 : K;
     const size_t nin = (size_t)D * N + nc + nr;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (h->dev != dev) { h->din = DevBuf(); h->dout = DevBuf(); h->dev = dev; }     // buffers belong to the device they were made on
     if (h->din.ensure((nin + 1) * sizeof(double)) || h->dout.ensure(((size_t)nout + 1) * sizeof(double))) {
         fprintf(stderr, "libTrajectoryConstraints (B200): %s\n", g_err);
         return res;

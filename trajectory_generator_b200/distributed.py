@@ -55,9 +55,10 @@ def all_gather_rows(rows, total=None, group=None):
     return torch.cat(parts, 0)
 
 
-def solve_sharded(spec, par, x0, maxiter=100, ftol=1e-6, jacobian="analytic", group=None):
+def solve_sharded(spec, par, x0, maxiter=100, ftol=1e-6, jacobian="fd", group=None):
     """Solve a batch that is replicated on every rank's HOST (numpy par [B,P], x0 [B,n]): each rank solves its
-    contiguous shard on its own GPU and all ranks return the full result (dict of numpy arrays)."""
+    contiguous shard on its own GPU and all ranks return the full result (dict of numpy arrays).  `jacobian`
+    defaults to "fd" like the drop-in class (the mode that follows the reference's iterates)."""
     import torch
     import torch.distributed as dist
     from . import batch

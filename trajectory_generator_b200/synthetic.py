@@ -26,11 +26,27 @@ OBJECTIVE = {"C2": "minimal_velocity_and_time_path", "C3": "minimal_velocity_and
 class Batch:
     def __init__(self, name, spec, par, x0, raw):
         self.name, self.spec, self.par, self.x0, self.raw = name, spec, par, x0, raw
-        self.layout = pk.Layout(spec)
-        assert par.shape[1] == self.layout.P and x0.shape[1] == self.layout.n
+        self._layout = None
+
+    @property
+    def layout(self):
+        """Row / parameter offsets of the shape (asks the native library: tg_layout).  Lazy, so that generating a
+        batch and rebuilding its containers (the CPU reference arm of bench.py) never loads the CUDA library."""
+        if self._layout is None:
+            self._layout = pk.Layout(self.spec)
+            assert self.par.shape[1] == self._layout.P and self.x0.shape[1] == self._layout.n
+        return self._layout
 
     def __len__(self):
         return self.par.shape[0]
+
+    def take(self, indices):
+        """The problems `indices` as a batch of their own (same descriptor; raw fields sliced along the batch axis)."""
+        idx = np.asarray(indices, dtype=np.int64)
+        B = len(self)
+        raw = {k: (v[idx] if isinstance(v, np.ndarray) and v.ndim >= 1 and v.shape[0] == B else v)
+               for k, v in self.raw.items()}
+        return Batch(self.name, self.spec, np.ascontiguousarray(self.par[idx]), np.ascontiguousarray(self.x0[idx]), raw)
 
 
 def _spec(d, N, objective, **flags):
@@ -271,6 +287,25 @@ def container_for(batch, i):
                        Waypoint(location=_col(r["goal"][i]), velocity=_col(r["v1"][i]))))
     cc = ConstraintsContainer(wd, DerivativeBounds(r["vmax"], r["amax"]), TurningBound(float(r["turn"][i]), r["turn_kind"]))
     return 2, cc, dict(num_intervals_free_space=5)
+
+
+def c1_problem():
+    """Config C1 (BASELINE configs[0]): the literal single problem of test_2D_trajectory.py:24-80 -- 2-D, three
+    corridors, start / end waypoints with velocity, v_max 30, a_max 100, `minimal_time_path`,
+    num_intervals_free_space = 10.  Returns (dimension, ConstraintsContainer, generate kwargs)."""
+    from .constraint_data_structures import get2DRotationAndTranslationFromPoints
+    pts = [_col(p) for p in ((-5, 0), (0, 5), (0, -5), (5, 0))]
+    dims = [(3, 2), (2, 3), (3, 2)]
+    sfcs = []
+    for i in range(3):
+        R, T, Ln = get2DRotationAndTranslationFromPoints(pts[i], pts[i + 1])
+        sfcs.append(SFC(np.array([[Ln + dims[i][0]], [dims[i][1]]]), T, R))
+    sfc = SFC_Data(tuple(sfcs), np.concatenate(pts, 1), 1, intervals_per_corridor=np.array([1, 1, 1]))
+    wd = WaypointData((Waypoint(location=_col((-5, 0)), velocity=_col((0, 15))),
+                       Waypoint(location=_col((5, 0)), velocity=_col((0, 10)))))
+    cc = ConstraintsContainer(waypoint_constraints=wd, derivative_constraints=DerivativeBounds(30, 100),
+                              turning_constraint=None, sfc_constraints=sfc, obstacle_constraints=None)
+    return 2, cc, dict(objective_function_type="minimal_time_path", num_intervals_free_space=10)
 
 
 def evaluation_points(batch, seed=99):
