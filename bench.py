@@ -618,7 +618,7 @@ def main():
     for k in head:
         if k.endswith("_mode"):
             line[k] = head[k]
-    line["config"]["schedule"] = "fused persistent kernel" if args.fused else "lock-step stage kernels"
+    line["schedule"] = "fused persistent kernel" if args.fused else "lock-step stage kernels"
     line["clocks"] = sampler.summary()
     do_cpu = G.world == 1 and not args.no_cpu_baseline and cpu_path_available()
     if do_cpu:

@@ -36,6 +36,9 @@ extern "C" {
 int tg_spec_count(void);
 /* fills out[] with struct TgLayout (all ints, field order of tg_spec.h); returns its length */
 int tg_layout(const int *spec, int *out, int cap);
+/* index (1..) of the kernel instantiation with a compile-time descriptor that serves `spec` (the BASELINE.json
+ * shapes, csrc/tg_shape.h), 0 when the shape runs the generic kernels.  Results are bit-identical either way. */
+int tg_fixed_shape_index(const int *spec);
 /* message of the last failing call on this thread ("" if none) */
 const char *tg_last_error(void);
 /* 0 when a CUDA device with an sm_100a image is usable, else an error code */

@@ -248,3 +248,26 @@ def test_batched_problem_constructor_plumbing(native_lib, monkeypatch):
     # a field of the extended set goes through the constructor's keyword pass-through
     bp = batched.BatchedProblem(2, t(r["start"]), t(r["goal"]), None, t(r["v1"]), start_direction=t(r["v0"]), max_jerk=3.0)
     assert bp.spec[batched.pk.SP_START_DIR] == 1 and bp.spec[batched.pk.SP_DB_JERK] == 1 and bp.layout.nws == 1
+
+
+def test_fixed_shape_descriptors_are_the_synthetic_configurations(native_lib):
+    """csrc/tg_shape.h lists the BASELINE shapes whose kernels are instantiated with a compile-time descriptor:
+    each must equal the descriptor synthetic.py (and pack_problem) builds for that configuration, and other shapes
+    must fall through to the generic kernels."""
+    import ctypes
+    from trajectory_generator_b200 import synthetic as syn
+    import problems
+    f = native_lib.tg_fixed_shape_index
+    f.argtypes = [ctypes.POINTER(ctypes.c_int)]; f.restype = ctypes.c_int
+    got = {}
+    for name in syn.CONFIGS:
+        spec = np.ascontiguousarray(syn.make(name, 2).spec, dtype=np.int32)
+        got[name] = f(spec.ctypes.data_as(ctypes.POINTER(ctypes.c_int)))
+    assert got == {"C2": 1, "C3": 2, "C4": 3, "C5a": 4, "C5c": 5}
+    from trajectory_generator_b200.problem import pack_problem
+    d, cc, kw = problems.sfc3d(helpers.product_namespace())           # shipped 3-corridor problem: not a fixed shape
+    pp = pack_problem(d, cc, kw["objective_function_type"])
+    assert f(np.ascontiguousarray(pp.spec, dtype=np.int32).ctypes.data_as(ctypes.POINTER(ctypes.c_int))) == 0
+    d, cc, kw = problems.obstacles8(helpers.product_namespace())      # the C2 shape through the drop-in packer
+    pp = pack_problem(d, cc)
+    assert f(np.ascontiguousarray(pp.spec, dtype=np.int32).ctypes.data_as(ctypes.POINTER(ctypes.c_int))) == 1

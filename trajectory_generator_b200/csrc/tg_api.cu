@@ -95,6 +95,8 @@ extern "C" int tg_layout(const int *spec, int *out, int cap)
     return cnt;
 }
 
+extern "C" int tg_fixed_shape_index(const int *spec) { return spec ? tg_fixed_index(spec) : 0; }
+
 extern "C" const char *tg_last_error(void) { return g_err; }
 extern "C" unsigned long long tg_launch_count(void) { return g_launches.load(); }
 void tg_note_launch(int count) { g_launches += (unsigned long long)count; }

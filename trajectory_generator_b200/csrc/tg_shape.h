@@ -10,6 +10,59 @@ struct TgShape {
     TgLayout L;
 };
 
+// ---------------------------------------------------------------------------
+// Shapes with kernel instantiations of their own.  The stage kernels are templates on FIX: 0 = the descriptor is a
+// kernel argument (any shape); k > 0 = the descriptor is the compile-time constant below, so the whole TgLayout
+// (sizes, row / parameter offsets, which constraint blocks exist) folds into the code: workspace arrays sit at
+// constant offsets, absent constraint kinds are compiled out, loop bounds are known.  Same arithmetic in the same
+// order: results are bit-identical to the generic instantiation.  The list holds the BASELINE.json configurations
+// (trajectory_generator_b200/synthetic.py builds the same descriptors; tests/test_packing.py compares them).
+// ---------------------------------------------------------------------------
+#define TG_FIXED_SHAPES 5
+enum { TG_FIX_C2 = 1, TG_FIX_C3, TG_FIX_C4, TG_FIX_C5A, TG_FIX_C5C };
+TG_HD constexpr int tg_fixed_spec(int fix, int field)
+{
+    constexpr int T[TG_FIXED_SHAPES][TG_SP_COUNT] = {
+        // C2: 2-D, 8 control points, start / end velocity, v_max, a_max, angular-rate bound, 8 obstacles
+        {2, 8, 5, 0, 0, 0, 1, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 1, 0, 0, 0, 2, 0, 0, 0, 0, 0, 0, 0, 0, 0, 8},
+        // C3: 2-D, 17 control points, two intermediate waypoints with velocities, v_max, curvature bound
+        {2, 17, 5, 0, 0, 0, 1, 0, 0, 1, 0, 2, 1, 0, 1, 0, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0},
+        // C4: 3-D, 11 control points, start velocity, zero-velocity end, v_max, a_max, 4 corridors x 2 intervals
+        {3, 11, 2, 0, 1, 0, 1, 0, 0, 0, 0, 0, 0, 0, 1, 0, 0, 1, 0, 0, 0, 0, 4, 2, 2, 2, 2, 0, 0, 0, 0, 0},
+        // C5a / C5c: 2-D, 8 control points, start / end velocity, v_max, a_max, angular-rate / curvature bound
+        {2, 8, 5, 0, 0, 0, 1, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 1, 0, 0, 0, 2, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0},
+        {2, 8, 5, 0, 0, 0, 1, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}};
+    return T[fix - 1][field];
+}
+
+// index of the fixed shape equal to `sp`, 0 if none (host)
+static inline int tg_fixed_index(const int *sp)
+{
+    for (int k = 1; k <= TG_FIXED_SHAPES; k++) {
+        bool same = true;
+        for (int i = 0; i < TG_SP_COUNT; i++) same = same && sp[i] == tg_fixed_spec(k, i);
+        if (same) return k;
+    }
+    return 0;
+}
+
+#if defined(__CUDACC__)
+// descriptor and layout a stage kernel works with: the kernel argument (FIX == 0) or compile-time constants
+template <int FIX>
+static __device__ __forceinline__ void tg_resolve_shape(const int *arg_sp, const TgLayout &arg_L, int *fsp, TgLayout *fL,
+                                                        const int **sp, const TgLayout **L)
+{
+    if (FIX > 0) {
+#pragma unroll
+        for (int i = 0; i < TG_SP_COUNT; i++) fsp[i] = tg_fixed_spec(FIX > 0 ? FIX : 1, i);
+        tg_make_layout(fsp, fL);
+        *sp = fsp; *L = fL;
+    } else {
+        *sp = arg_sp; *L = &arg_L;
+    }
+}
+#endif
+
 // round bookkeeping of the lock-step solve (device memory).  Round r works through list[r & 1] (count[r & 1]
 // problem indices, handed out through the head_* cursors) and the QP stage appends the problems that are not
 // finished to the other list; `done` counts finished problems (polled by the host).
