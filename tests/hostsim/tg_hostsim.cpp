@@ -64,8 +64,10 @@ extern "C" void hs_fd_derivatives(const int *spec, const double *par, const doub
     tg_sqp_carve(L, ws.data(), &W);
     tg_sqp_begin(L, W, x, 100, 1e-6, TG_SQP_FD_JACOBIAN);
     for (int i = 0; i < L.n; i++) { W.xl[i] = xl[i]; W.xu[i] = xu[i]; }
-    TgJac sink = {W.A, 1, W.lda, 0};
+    TgJac sink = {W.A, 1, W.lda, 2};          // the solver's A: every row except the corridor rows
+    TgJac full = {J, L.n, 1, 0};              // corridor rows (constant) straight into the dense output
     double f;
+    if (L.n_sfc) { if (L.d == 2) tg_jac_sfc<2>(L, spec, par, full); else tg_jac_sfc<3>(L, spec, par, full); }
     if (L.d == 2) {
         tg_linear_jacobian_d<2>(L, spec, par, sink);
         f = tg_sqp_evaluate<2>(L, spec, par, W, false);
@@ -77,7 +79,8 @@ extern "C" void hs_fd_derivatives(const int *spec, const double *par, const doub
     }
     for (int i = 0; i < L.n; i++) {
         g[i] = W.g[i];
-        for (int j = 0; j < L.m; j++) J[j * L.n + i] = W.A[i * W.lda + j];
+        for (int j = 0; j < L.m; j++)
+            if (!tg_is_sfc_row(W, j)) J[j * L.n + i] = W.A[i * W.lda + tg_arow(W, j)];
     }
 }
 #endif

@@ -114,6 +114,15 @@ def sfc3d_four(ns):
     return 3, cc, dict(objective_function_type="minimal_velocity_path")
 
 
+def sfc_obstacles3d(ns):
+    """Coverage problem (not from a demo): the 4-corridor C4 shape with two spheres inside the corridors -- corridor
+    rows AND rows behind them in one problem (the solver stores no corridor rows: the obstacle rows move up)."""
+    Ob = ns["Obstacle"]
+    d, cc, kw = sfc3d_four(ns)
+    cc.obstacle_constraints = [Ob(center=_col(10, 4.5, 2.2), radius=0.5), Ob(center=_col(17, 8.5, 3), radius=0.6)]
+    return d, cc, kw
+
+
 def bicycle3(ns):
     """bicycle_trajectory_3.py (config C5, angular-rate variant)."""
     W, WD, DB, TB = ns["Waypoint"], ns["WaypointData"], ns["DerivativeBounds"], ns["TurningBound"]
@@ -173,12 +182,12 @@ def features2d(ns):
 
 ALL = dict(c1_sfc2d=c1_sfc2d, c1_curvature=c1_curvature, obstacle2d=obstacle2d, obstacles8=obstacles8,
            intermediate_waypoints=intermediate_waypoints, intermediate_curvature=intermediate_curvature,
-           sfc3d=sfc3d, sfc3d_four=sfc3d_four, bicycle3=bicycle3, unicycle2=unicycle2,
+           sfc3d=sfc3d, sfc3d_four=sfc3d_four, sfc_obstacles3d=sfc_obstacles3d, bicycle3=bicycle3, unicycle2=unicycle2,
            bicycle_tangential=bicycle_tangential, features3d=features3d, features2d=features2d)
 
 # problems whose reference solve finishes in a few seconds (solve results are recorded for these)
-SOLVE = ("c1_sfc2d", "c1_curvature", "obstacle2d", "obstacles8", "sfc3d", "sfc3d_four", "bicycle3", "unicycle2",
-         "intermediate_waypoints")
+SOLVE = ("c1_sfc2d", "c1_curvature", "obstacle2d", "obstacles8", "sfc3d", "sfc3d_four", "sfc_obstacles3d", "bicycle3",
+         "unicycle2", "intermediate_waypoints")
 
 
 def test_point(x0, d, N, seed):

@@ -197,8 +197,11 @@ TG_HD int tg_any(int pred)
 
 // ---------------------------------------------------------------------------
 // Jacobian sink.  Element (row r, column i) lives at p[row(r) * rs + i * cs].
-// compact != 0: only nonlinear rows are stored, re-indexed densely (the M1
-// output layout); compact == 0: every row r is stored (the SQP's A matrix).
+// compact == 1: only nonlinear rows are stored, re-indexed densely (the M1
+// output layout); compact == 0: every row r is stored; compact == 2: every row
+// except the corridor rows, the rows behind them moved up (the SQP's A matrix:
+// a corridor normal has 4 d structural non-zeros that are regenerated from the
+// corridor's rotation and the MINVO matrix where they are needed, tg_sqp.h).
 // ---------------------------------------------------------------------------
 struct TgJac {
     double *p;
@@ -216,7 +219,14 @@ TG_HD int tg_nlrow(const TgLayout &L, int r)
 
 TG_HD double *tg_jrow(const TgJac &J, const TgLayout &L, int r)
 {
-    return J.p + (J.compact ? tg_nlrow(L, r) : r) * J.rs;
+    // rows in front of the corridor block (compact == 2 stores them unmoved); rows behind it go through tg_jrow_hi
+    return J.p + (J.compact == 1 ? tg_nlrow(L, r) : r) * J.rs;
+}
+
+// row r >= L.r_obs (behind the corridor block)
+TG_HD double *tg_jrow_hi(const TgJac &J, const TgLayout &L, int r)
+{
+    return J.p + (J.compact == 1 ? tg_nlrow(L, r) : J.compact == 2 ? r - 2 * L.n_sfc : r) * J.rs;
 }
 
 // ---------------------------------------------------------------------------
@@ -1149,7 +1159,7 @@ TG_FN void tg_rows_obstacles(const TgLayout &L, const int *sp, const double *par
 #pragma unroll
             for (int c = 0; c < D; c++) ctr[c] = par[L.p_obs_c + c * K + i];
             tg_hull_distance<D>(x, N, jb, ctr, par[L.p_obs_r + i], gl);
-            double *row = tg_jrow(*J, L, L.r_obs + i);
+            double *row = tg_jrow_hi(*J, L, L.r_obs + i);
             const int cs = J->cs;
 #pragma unroll
             for (int c = 0; c < D; c++)
@@ -1171,7 +1181,7 @@ TG_FN void tg_zero_nonlinear_rows(const TgLayout &L, const TgJac &J)
     #pragma unroll 1
     for (int r = 0; r < L.m; r++) {
         if (tg_nlrow(L, r) < 0) continue;
-        double *row = tg_jrow(J, L, r);
+        double *row = r >= L.r_obs ? tg_jrow_hi(J, L, r) : tg_jrow(J, L, r);
         #pragma unroll 1
         for (int i = lane; i < L.n; i += TG_NL) row[i * J.cs] = 0;
     }
@@ -1281,8 +1291,9 @@ TG_EVAL_FN void tg_fd_turning(const TgLayout &L, const int *sp, const double *pa
 // scr: K nint + 4 d N doubles (the first K nint are the base distances, as tg_rows_obstacles leaves them)
 template <int D>
 TG_EVAL_FN void tg_fd_obstacles(const TgLayout &L, const double *par, const double *x, const double *xl, const double *xu,
-                           const double *cbase, double *A, int lda, double *scr)
+                           const double *cbase, double *A, int lda, int arow0, double *scr)
 {
+    // arow0: row of A that holds the first obstacle row (L.r_obs, or less when A stores no corridor rows)
     const int N = L.N, nint = L.nint, K = L.n_obs, lane = TG_LANE(), n = L.n;
     double *base = scr, *pert = scr + K * nint;
     #pragma unroll 1
@@ -1323,7 +1334,7 @@ TG_EVAL_FN void tg_fd_obstacles(const TgLayout &L, const double *par, const doub
                 const double dx = (x[i] + tg_fd_step(x[i], xl[i], xu[i])) - x[i];
                 entry = (best - cbase[L.r_obs + k]) / dx;
             }
-            A[i * lda + L.r_obs + k] = entry;
+            A[i * lda + arow0 + k] = entry;
         }
         TG_SYNC();
     }
@@ -1334,7 +1345,7 @@ template <int D>
 TG_FN void tg_linear_jacobian_d(const TgLayout &L, const int *sp, const double *par, const TgJac &J)
 {
     tg_jac_location(L, sp, par, J);
-    if (L.n_sfc) tg_jac_sfc<D>(L, sp, par, J);
+    if (L.n_sfc && J.compact != 2) tg_jac_sfc<D>(L, sp, par, J);
     TG_SYNC();
 }
 

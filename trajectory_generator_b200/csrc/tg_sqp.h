@@ -46,7 +46,7 @@ enum { TG_ST_INIT = 0, TG_ST_QP, TG_ST_LS, TG_ST_UPDATE, TG_ST_DONE };
 #define TG_CTL_DOUBLES ((int)((sizeof(TgSqpCtl) + 7) / 8))
 
 struct TgSqpWs {
-    int n, n1, m, lda, ldq, nc;      // nc = m + 2*n1 (constraints incl. variable bounds)
+    int n, n1, m, lda, ldq, nc;      // nc = m + 2*n1 (constraints incl. variable bounds); lda: rows of A (no corridor rows)
     int sfc0, nsfc, sfc_npts, cpN, cpd;      // corridor rows [sfc0, sfc0 + 2 nsfc): row -> interval -> the only non-zero columns
     TgSqpCtl *ctl;
     // persistent
@@ -90,7 +90,8 @@ TG_HD void tg_sqp_carve4(const TgLayout &L, double *prefix, double *pbase, doubl
 {
     const int n = L.n, n1 = n + 1, m = L.m;
     TgSqpWs w;
-    w.n = n; w.n1 = n1; w.m = m; w.lda = tg_odd(m > 0 ? m : 1); w.ldq = tg_odd(n1); w.nc = m + 2 * n1;
+    const int ma = m - 2 * L.n_sfc;       // rows stored in A
+    w.n = n; w.n1 = n1; w.m = m; w.lda = tg_odd(ma > 0 ? ma : 1); w.ldq = tg_odd(n1); w.nc = m + 2 * n1;
     w.sfc0 = L.r_sfcl; w.nsfc = L.n_sfc; w.sfc_npts = 4 * L.nint; w.cpN = L.N; w.cpd = L.d;
     size_t o = 0;
     double *base = prefix;
@@ -155,6 +156,34 @@ TG_HD size_t tg_sqp_carve(const TgLayout &L, double *base, TgSqpWs *W)
 TG_HD bool tg_finite(double v) { return v - v == 0; }
 
 // ---------------------------------------------------------------------------
+// A holds the Jacobian rows of every constraint EXCEPT the corridor rows (column i at A[i * lda + row], rows behind
+// the corridor block moved up by 2 nsfc).  A corridor row (CF/sfc_constraints.py:53-77: lb <= R' Q <= ub on the
+// MINVO points Q of an interval) has 4 d structural non-zeros, rot[rr][c] * M_minvo[l][k] at control point j + l of
+// coordinate c; they are regenerated from the per-interval rotation table (written once by stage LS) -- the same
+// product tg_jac_sfc forms -- instead of being stored: C4's state shrinks from 62 KB to 23 KB per problem.
+// ---------------------------------------------------------------------------
+TG_HD bool tg_is_sfc_row(const TgSqpWs &W, int p) { return p >= W.sfc0 && p < W.sfc0 + 2 * W.nsfc; }
+TG_HD int tg_arow(const TgSqpWs &W, int p) { return p < W.sfc0 ? p : p - 2 * W.nsfc; }       // p not a corridor row
+
+// entry (row p, column i < n) of a corridor row; rot: per-interval rotation table
+TG_HD double tg_sfc_entry(const TgSqpWs &W, const double *rot, int p, int i)
+{
+    const int D = W.cpd, N = W.cpN, npts = W.sfc_npts;
+    if (i >= D * N) return 0.0;
+    int q = p - W.sfc0;
+    const bool upper = q >= W.nsfc;
+    if (upper) q -= W.nsfc;
+    const int rr = q / npts, idx = q - rr * npts, j = idx >> 2, k = idx & 3;
+    const int c = i / N, l = i - c * N - j;
+    if (l < 0 || l > 3) return 0.0;
+    const double v = rot[j * D * D + rr * D + c] * tg_minvo_py(l, k);
+    return upper ? -v : v;
+}
+
+// coefficient of the slack variable of the augmented problem in row j (SLSQP: -c for equalities, max(-c, 0) else)
+TG_HD double tg_slack_coeff(const TgSqpWs &W, int meq, int j) { return j < meq ? -W.c[j] : fmax(-W.c[j], 0.0); }
+
+// ---------------------------------------------------------------------------
 // LDL^T rank-one update  B <- B + sigma z z^T  (composite-t method of Fletcher &
 // Powell, as used by SLSQP's LDL routine).  Lm: unit lower factor, column i at
 // Lm[i*n + j] (j > i); Dd: diagonal.  z is destroyed; w is scratch (n), sc is
@@ -185,6 +214,23 @@ TG_QFN void tg_ldl_update(int n, double sigma, double *z, double *Lm, double *Dd
     #pragma unroll 1
     for (int i = lane; i < n; i += TG_NL) vf[i] = z[i];
     TG_SYNC();
+#if defined(__CUDA_ARCH__) && TG_GS >= 32
+    // one warp, v in registers (entries lane and lane + 32), the pivot handed round with a shuffle (see the back
+    // substitution of tg_qp_directions); same operations in the same order
+    if (TG_SERIAL_ACTIVE()) {
+        const int l32 = lane & 31;
+        double v0 = l32 < n ? vf[l32] : 0.0, v1 = l32 + 32 < n ? vf[l32 + 32] : 0.0;
+        #pragma unroll 2
+        for (int i = 0; i < n - 1; i++) {
+            const double vv = __shfl_sync(0xffffffffu, i < 32 ? v0 : v1, i & 31);
+            const double *Li = Lm + i * n;
+            if (l32 > i && l32 < n) v0 -= vv * Li[l32];
+            if (l32 + 32 > i && l32 + 32 < n) v1 -= vv * Li[l32 + 32];
+        }
+        if (l32 < n) vf[l32] = v0;
+        if (l32 + 32 < n) vf[l32 + 32] = v1;
+    }
+#else
     if (TG_SERIAL_ACTIVE()) {
         #pragma unroll 1
         for (int i = 0; i < n - 1; i++) {
@@ -194,6 +240,7 @@ TG_QFN void tg_ldl_update(int n, double sigma, double *z, double *Lm, double *Dd
             TG_SERIAL_SYNC();
         }
     }
+#endif
     TG_SYNC();
     // ---- B: delta_i = v_i / d_i ; t'_i ; alpha_i = t'_i / t_i, beta_i = delta_i / t'_i, gamma_i = t_i / t'_i
     #pragma unroll 1
@@ -283,12 +330,16 @@ TG_QFN void tg_ldl_apply(int n, const double *Lm, const double *Dd, const double
 // ---------------------------------------------------------------------------
 #define TG_QP_OK 1
 
-TG_HD void tg_qp_normal(const TgSqpWs &W, int nq, int p, double *np)
+TG_HD void tg_qp_normal(const TgSqpWs &W, int nq, int meq, int p, double *np)
 {
     const int lane = TG_LANE();
-    if (p < W.m) {
+    if (p < W.m && tg_is_sfc_row(W, p)) {
         #pragma unroll 1
-        for (int i = lane; i < nq; i += TG_NL) np[i] = W.A[i * W.lda + p];
+        for (int i = lane; i < nq; i += TG_NL) np[i] = i < W.n ? tg_sfc_entry(W, W.rotq, p, i) : tg_slack_coeff(W, meq, p);
+    } else if (p < W.m) {
+        const int pa = tg_arow(W, p);
+        #pragma unroll 1
+        for (int i = lane; i < nq; i += TG_NL) np[i] = W.A[i * W.lda + pa];
     } else {
         const int q = p - W.m;
         const int i0 = q < W.n1 ? q : q - W.n1;
@@ -340,6 +391,22 @@ TG_QFN void tg_qp_directions(const TgSqpWs &W, int nq, int iq, double &d2n, doub
         W.z[i] = h;
     }
     // back substitution R rq = d1 (column oriented; hw holds the running right-hand side, rdi = 1 / diag R)
+#if defined(__CUDA_ARCH__) && TG_GS >= 32
+    // One warp, the running right-hand side in registers (entries lane and lane + 32), the pivot handed round with
+    // a shuffle: no shared-memory round trip and no warp sync per step.  Same operations in the same order.
+    if (TG_SERIAL_ACTIVE()) {
+        const int l32 = lane & 31;
+        double h0 = l32 < iq ? W.hw[l32] : 0.0, h1 = l32 + 32 < iq ? W.hw[l32 + 32] : 0.0;
+        #pragma unroll 2
+        for (int j = iq - 1; j >= 0; j--) {
+            const double rj = __shfl_sync(0xffffffffu, j < 32 ? h0 : h1, j & 31) * W.rdi[j];
+            const double *Rj = W.R + tg_rp(j);
+            if (l32 == (j & 31)) W.rq[j] = rj;
+            if (l32 < j) h0 -= Rj[l32] * rj;
+            if (l32 + 32 < j) h1 -= Rj[l32 + 32] * rj;
+        }
+    }
+#else
     if (TG_SERIAL_ACTIVE()) {
         #pragma unroll 1
         for (int j = iq - 1; j >= 0; j--) {
@@ -350,6 +417,7 @@ TG_QFN void tg_qp_directions(const TgSqpWs &W, int nq, int iq, double &d2n, doub
             TG_SERIAL_SYNC();
         }
     }
+#endif
     TG_SYNC();
 }
 
@@ -528,7 +596,7 @@ TG_QFN int tg_qp_solve(const TgSqpWs &W, int nq, int meq, double rho, double &fl
                             if (W.iact[p]) continue;
                             const double cp = W.c[p];
                             double h = side ? -sq : sq, sc = fabs(cp) + sa;
-                            if (nq > n) { const double t = W.A[n * W.lda + p] * slack; h += t; sc += fabs(t); }
+                            if (nq > n) { const double t = fmax(-cp, 0.0) * slack; h += t; sc += fabs(t); }
                             const double sv = h + cp;
                             if (sv < -1e-13 * sc && (sv < best || (sv == best && p < ip))) { best = sv; ip = p; }
                         }
@@ -544,9 +612,10 @@ TG_QFN int tg_qp_solve(const TgSqpWs &W, int nq, int meq, double rho, double &fl
                 if (W.iact[p]) continue;
                 double sv, tol;
                 if (p < m) {
+                    const int pa = t;          // row of A: the corridor rows are not stored
                     double h = 0, sc = fabs(W.c[p]);
                     #pragma unroll 8
-                    for (int i = 0; i < nq; i++) { const double t = W.A[i * W.lda + p] * W.xq[i]; h += t; sc += fabs(t); }
+                    for (int i = 0; i < nq; i++) { const double t = W.A[i * W.lda + pa] * W.xq[i]; h += t; sc += fabs(t); }
                     sv = h + W.c[p];
                     tol = 1e-13 * sc;
                 } else {
@@ -575,7 +644,7 @@ TG_QFN int tg_qp_solve(const TgSqpWs &W, int nq, int meq, double rho, double &fl
                 return TG_QP_OK;
             }
         }
-        tg_qp_normal(W, nq, ip, W.np);
+        tg_qp_normal(W, nq, meq, ip, W.np);
         double uip = 0;
         double sv = tg_qp_value(W, nq, ip);
         #pragma unroll 1
@@ -645,7 +714,7 @@ template <int D>
 TG_FN double tg_sqp_evaluate(const TgLayout &L, const int *sp, const double *par, const TgSqpWs &W, bool derivs)
 {
     const double f = tg_objective(L, sp, W.x, derivs ? W.g : 0);
-    TgJac sink = {W.A, 1, W.lda, 0};
+    TgJac sink = {W.A, 1, W.lda, 2};
     tg_constraints_d<D>(L, sp, par, W.x, W.c, derivs ? &sink : 0, W.scratch);
     TG_SYNC();
     return f;
@@ -678,7 +747,7 @@ TG_FN void tg_sqp_fd_derivatives(const TgLayout &L, const int *sp, const double 
     }
     // the heavy blocks: item-parallel sweeps (tg_eval.h)
     if (L.n_turn) tg_fd_turning<D>(L, sp, par, W.x, W.xl, W.xu, W.c[L.r_turn], W.A, W.lda, W.scratch);
-    if (L.n_obs) tg_fd_obstacles<D>(L, par, W.x, W.xl, W.xu, W.c, W.A, W.lda, W.scratch);
+    if (L.n_obs) tg_fd_obstacles<D>(L, par, W.x, W.xl, W.xu, W.c, W.A, W.lda, L.r_obs - 2 * L.n_sfc, W.scratch);
     (void)m;
 }
 
@@ -727,7 +796,7 @@ TG_FN void tg_sqp_stage_ls(const TgLayout &L, const int *sp, const double *par, 
     const bool init = ctl.state == TG_ST_INIT;
     if (init || ctl.state == TG_ST_LS) {
         if (init) {
-            TgJac sink = {W.A, 1, W.lda, 0};
+            TgJac sink = {W.A, 1, W.lda, 2};
             tg_linear_jacobian_d<D>(L, sp, par, sink);
             // rotation of the corridor that owns each interval, for the QP stage's violation scans
             if (L.n_sfc) {
@@ -790,7 +859,7 @@ TG_FN void tg_sqp_stage_der(const TgLayout &L, const int *sp, const double *par,
         ctl.nfev += L.n;
     } else {
         const double f = tg_objective(L, sp, W.x, W.g);
-        TgJac sink = {W.A, 1, W.lda, 0};
+        TgJac sink = {W.A, 1, W.lda, 2};
         tg_constraints_d<D>(L, sp, par, W.x, W.c, &sink, W.scratch);
         TG_SYNC();
         (void)f;
@@ -808,6 +877,12 @@ TG_QFN void tg_sqp_stage_qp(const TgLayout &L, const TgSqpWs &W)
     const double acc = ctl.acc, tol = 10 * ctl.acc;
     double h1, h2, h3;
     double fl = 0;       // model count of the stage's fp64 operations (2 per multiply-add), for the roofline report
+    if (W.nsfc) {
+        // rotation of the corridor that owns each interval: regenerates corridor normals and serves the violation scans
+        #pragma unroll 1
+        for (int q = lane; q < (W.sfc_npts >> 2) * W.cpd * W.cpd; q += TG_NL) W.rotq[q] = W.rot[q];
+        TG_SYNC();
+    }
     if (ctl.state == TG_ST_UPDATE) {
         // ---- convergence test after the step
         double sn = 0;
@@ -823,7 +898,10 @@ TG_QFN void tg_sqp_stage_qp(const TgLayout &L, const TgSqpWs &W)
             for (int i = lane; i < n; i += TG_NL) {
                 double h = W.g[i];
                 #pragma unroll 2
-                for (int k = 0; k < ctl.nract; k++) { const int j = W.ract[k]; h -= W.A[i * W.lda + j] * W.r[j]; }
+                for (int k = 0; k < ctl.nract; k++) {
+                    const int j = W.ract[k];
+                    h -= (tg_is_sfc_row(W, j) ? tg_sfc_entry(W, W.rotq, j, i) : W.A[i * W.lda + tg_arow(W, j)]) * W.r[j];
+                }
                 W.u[i] = h - W.gl[i];
             }
             TG_SYNC();
@@ -851,11 +929,6 @@ TG_QFN void tg_sqp_stage_qp(const TgLayout &L, const TgSqpWs &W)
         }
     }
     if (ctl.state == TG_ST_QP) {
-        if (W.nsfc) {
-            #pragma unroll 1
-            for (int q = lane; q < (W.sfc_npts >> 2) * W.cpd * W.cpd; q += TG_NL) W.rotq[q] = W.rot[q];
-            TG_SYNC();
-        }
         do {
             if (ctl.need_reset) {
                 // ---- reset the BFGS factor to the identity
@@ -899,7 +972,8 @@ TG_QFN void tg_sqp_stage_qp(const TgLayout &L, const TgSqpWs &W)
                 if (attempt >= 1 && nq == n) {
                     ctl.badlin = 1;
                     #pragma unroll 1
-                    for (int j = lane; j < m; j += TG_NL) W.A[n * W.lda + j] = j < meq ? -W.c[j] : fmax(-W.c[j], 0.0);
+                    for (int j = lane; j < m; j += TG_NL)
+                        if (!tg_is_sfc_row(W, j)) W.A[n * W.lda + tg_arow(W, j)] = tg_slack_coeff(W, meq, j);
                     if (lane == 0) { W.g[n] = 0; W.u[n] = 0; W.v[n] = 1; }
                     TG_SYNC();
                     nq = n1;
@@ -930,7 +1004,10 @@ TG_QFN void tg_sqp_stage_qp(const TgLayout &L, const TgSqpWs &W)
             for (int i = lane; i < n; i += TG_NL) {
                 double h = W.g[i];
                 #pragma unroll 2
-                for (int k = 0; k < ctl.nract; k++) { const int j = W.ract[k]; h -= W.A[i * W.lda + j] * W.r[j]; }
+                for (int k = 0; k < ctl.nract; k++) {
+                    const int j = W.ract[k];
+                    h -= (tg_is_sfc_row(W, j) ? tg_sfc_entry(W, W.rotq, j, i) : W.A[i * W.lda + tg_arow(W, j)]) * W.r[j];
+                }
                 W.gl[i] = h;
                 W.s[i] = W.xq[i];
                 W.x0[i] = W.x[i];
