@@ -367,6 +367,8 @@ TG_HD double tg_qp_value(const TgSqpWs &W, int nq, int p)
 // d = J' np ; z = J2 d2 ; rq = R^-1 d1 ; returns |d2|^2 (= z.np) and |d|^2
 TG_QFN void tg_qp_directions(const TgSqpWs &W, int nq, int iq, double &d2n, double &dn)
 {
+    // (visiting only the non-zero entries of a sparse normal -- a bit mask of them, one bit scan per term -- was
+    // measured: same numbers, QP stage +2 .. 3 % on C2 / C4: the stage is bound by dependent latency, not by issue slots)
     const int lane = TG_LANE(), ld = W.ldq;
     double a = 0, b = 0;
     #pragma unroll 1
@@ -383,6 +385,8 @@ TG_QFN void tg_qp_directions(const TgSqpWs &W, int nq, int iq, double &d2n, doub
     d2n = tg_wsum(a);
     dn = tg_wsum(b);
     TG_SYNC();
+    // (64-lane groups: forming z on the second warp while the first runs the back substitution below was measured
+    // neutral, +-0.5 %)
     #pragma unroll 1
     for (int i = lane; i < nq; i += TG_NL) {
         double h = 0;
@@ -493,7 +497,7 @@ TG_QFN void tg_qp_drop(const TgSqpWs &W, int nq, int &iq, int l)
     TG_SYNC();
 }
 
-TG_QFN int tg_qp_solve(const TgSqpWs &W, int nq, int meq, double rho, double &fl, int &nract, double dfloor)
+TG_QFN int tg_qp_solve(const TgSqpWs &W, const double *Lsrc, int nq, int meq, double rho, double &fl, int &nract, double dfloor)
 {
     const int lane = TG_LANE(), n = W.n, ld = W.ldq, m = W.m;
     const int nc = m + 2 * W.n1;
@@ -506,7 +510,7 @@ TG_QFN int tg_qp_solve(const TgSqpWs &W, int nq, int meq, double rho, double &fl
     for (int i = 0; i < n - 1; i++) {
         const int bi = i * n - i * (i + 1) / 2 - i - 1;
         #pragma unroll 1
-        for (int j = i + 1 + lane; j < n; j += TG_NL) Ls[bi + j] = W.Lm[i * n + j];
+        for (int j = i + 1 + lane; j < n; j += TG_NL) Ls[bi + j] = Lsrc[i * n + j];
     }
     TG_SYNC();
     #pragma unroll 1
@@ -870,8 +874,16 @@ TG_FN void tg_sqp_stage_der(const TgLayout &L, const int *sp, const double *par,
     TG_SYNC();
 }
 
+// lm_far: the persistent state (W.Lm ...) lives in global memory (lock-step kernel of a shape whose state is not
+// staged in shared memory).  The factor L is then copied once into the storage of J (free until the QP is set up),
+// updated there, written back once and handed to the QP set-up from there, instead of being read five times and
+// written twice through L2.  Same arithmetic.
+template <bool LM_FAR>
 TG_QFN void tg_sqp_stage_qp(const TgLayout &L, const TgSqpWs &W)
 {
+    // the update's scratch (5 n doubles) comes from R's storage when L sits in J's
+    const bool lm_far = LM_FAR && W.n1 * (W.n1 + 1) / 2 + 1 >= 5 * L.n;
+    bool lcopy = false;      // J's storage holds the current L
     const int lane = TG_LANE(), n = L.n, m = L.m, meq = L.meq, n1 = W.n1;
     TgSqpCtl ctl = *W.ctl;
     const double acc = ctl.acc, tol = 10 * ctl.acc;
@@ -905,7 +917,13 @@ TG_QFN void tg_sqp_stage_qp(const TgLayout &L, const TgSqpWs &W)
                 W.u[i] = h - W.gl[i];
             }
             TG_SYNC();
-            tg_ldl_apply(n, W.Lm, W.Dd, W.s, W.w, W.v);
+            if (lm_far) {
+                #pragma unroll 4
+                for (int q = lane; q < n * n; q += TG_NL) W.Jq[q] = W.Lm[q];
+                TG_SYNC();
+                lcopy = true;
+                tg_ldl_apply(n, W.Jq, W.Dd, W.s, W.w, W.v);
+            } else tg_ldl_apply(n, W.Lm, W.Dd, W.s, W.w, W.v);
             h1 = 0; h2 = 0;
             #pragma unroll 1
             for (int i = lane; i < n; i += TG_NL) { h1 += W.s[i] * W.u[i]; h2 += W.s[i] * W.v[i]; }
@@ -922,8 +940,16 @@ TG_QFN void tg_sqp_stage_qp(const TgLayout &L, const TgSqpWs &W)
             if (h1 == 0 || h2 == 0) ctl.need_reset = 1;
             else {
                 #pragma unroll 1
-                for (int pass = 0; pass < 2; pass++)
-                    tg_ldl_update(n, pass == 0 ? 1 / h1 : -1 / h2, pass == 0 ? W.u : W.v, W.Lm, W.Dd, W.w, W.Jq);
+                // (scratch of the update: 5 n doubles; with L in J's storage they come from R's, free until the QP set-up)
+                for (int pass = 0; pass < 2; pass++) {
+                    if (lm_far) tg_ldl_update(n, pass == 0 ? 1 / h1 : -1 / h2, pass == 0 ? W.u : W.v, W.Jq, W.Dd, W.w, W.R);
+                    else tg_ldl_update(n, pass == 0 ? 1 / h1 : -1 / h2, pass == 0 ? W.u : W.v, W.Lm, W.Dd, W.w, W.Jq);
+                }
+                if (lm_far) {
+                    #pragma unroll 4
+                    for (int q = lane; q < n * n; q += TG_NL) W.Lm[q] = W.Jq[q];
+                    TG_SYNC();
+                }
             }
             ctl.state = TG_ST_QP;
         }
@@ -945,6 +971,7 @@ TG_QFN void tg_sqp_stage_qp(const TgLayout &L, const TgSqpWs &W)
                     break;
                 }
                 #pragma unroll 1
+                lcopy = false;
                 for (int q = lane; q < n * n; q += TG_NL) W.Lm[q] = 0;
                 #pragma unroll 1
                 for (int i = lane; i < n1; i += TG_NL) W.Dd[i] = 1;
@@ -985,7 +1012,9 @@ TG_QFN void tg_sqp_stage_qp(const TgLayout &L, const TgSqpWs &W)
                     for (int i = 0; i < n; i++) dmax = fmax(dmax, W.Dd[i]);
                     dfloor = 1e-10 * dmax;
                 }
-                mode = tg_qp_solve(W, nq, meq, rho, fl, ctl.nract, dfloor);
+                // (one call site: the solver is inlined.  Only its first loop, which packs L next to J, reads Lsrc)
+                mode = tg_qp_solve(W, (lm_far && lcopy) ? W.Jq : W.Lm, nq, meq, rho, fl, ctl.nract, dfloor);
+                lcopy = false;        // the copy shared J's storage: the solve has overwritten it
                 if (attempt == 0 && mode == 6 && n == meq) mode = 4;
                 if (mode == TG_QP_OK) break;
                 if (mode != 4 && attempt < 6) attempt = 6;          // exits 6 / 3: straight to the last resort
@@ -1067,7 +1096,7 @@ TG_FN void tg_sqp_solve(const TgLayout &L, const int *sp, const double *par, dou
         const int st = W.ctl->state;
         if (st == TG_ST_DONE) break;
         if (st == TG_ST_INIT || st == TG_ST_LS) { tg_sqp_stage_ls<D>(L, sp, par, W, trace, trace_cap); tg_sqp_stage_der<D>(L, sp, par, W); }
-        else tg_sqp_stage_qp(L, W);
+        else tg_sqp_stage_qp<false>(L, W);
     }
     #pragma unroll 1
     for (int i = TG_LANE(); i < L.n; i += TG_NL) xio[i] = W.x[i];
