@@ -96,6 +96,11 @@ int tg_solve_host(const int *spec, int B, const double *par, double *x, double *
 int tg_solve_mixed_host(int nbuckets, const int *specs, const int *counts, const double *const *par,
                         double *const *x, double *const *f, int *const *status, int *const *nit,
                         int *const *violation, int maxiter, double ftol, int flags);
+/* the same with DEVICE pointers (par[k], x[k], f[k], ... are device buffers; the array of pointers itself is a host
+ * array): the buckets run on internal streams that fork from and join `stream`; nothing is copied */
+int tg_solve_mixed_batch(int nbuckets, const int *specs, const int *counts, const double *const *par, double *const *x,
+                         double *const *f, int *const *status, int *const *nit, int *const *violation, int maxiter,
+                         double ftol, int flags, void *stream);
 
 /*
  * Output sampling of a batch of cubic trajectories, device pointers:
@@ -113,6 +118,43 @@ int tg_solve_mixed_host(int nbuckets, const int *specs, const int *counts, const
 int tg_sample_batch(int d, int N, int B, const double *cps, long cps_stride, const double *scale, long scale_stride,
                     int derivative_order, int mode, int num_points, const double *offset, double dt,
                     double *out, long capacity, double *times, int *counts, void *stream);
+
+/* the same for B-splines of order 2 .. 5 (the reference's get_M_matrix, TG/matrix_evaluation.py:197-262;
+ * tg_sample_batch is order 3); derivative_order <= order */
+int tg_sample_batch_order(int order, int d, int N, int B, const double *cps, long cps_stride, const double *scale,
+                          long scale_stride, int derivative_order, int mode, int num_points, const double *offset,
+                          double dt, double *out, long capacity, double *times, int *counts, void *stream);
+
+/*
+ * One point (or r-th derivative) of one spline interval per item -- evaluate_point_on_interval /
+ * evaluate_point_derivative_on_interval (TG/matrix_evaluation.py:183-195), the primitive of the reference's waypoint
+ * closures: out[b][c] = cps[b][c][0..order] . M . T(t[b], tj[b], scale[b]).  cps[B][d][order+1], device pointers.
+ */
+int tg_interval_points_batch(int order, int d, int B, const double *cps, const double *t, const double *tj,
+                             const double *scale, int derivative_order, double *out, void *stream);
+
+/*
+ * Shape from geometry (SURVEY.md 8(f) f2 -> f3): intervals per corridor as SFC_Data chooses them
+ * (DS/safe_flight_corridor.py:78-88) from the corridor end points[B][d][ncorr+1]; ipc[B][ncorr], key[B] (optional) =
+ * the ipc values packed 8 bits each, equal for problems of one shape.  Device pointers.
+ */
+int tg_sfc_intervals_batch(int d, int ncorr, int B, const double *points, int min_per_corridor, int *ipc,
+                           long long *key, void *stream);
+
+/*
+ * Spline order converter (SmoothingSpline.generate_new_control_points,
+ * TG/spline_order_converter.py:22-34): for every old spline, control points x[b][d][N] of a B-spline of `order` that
+ * minimise the squared distance to the old spline over `resolution` samples with position, velocity and acceleration
+ * matched at both ends, solved with the batched SLSQP iteration (finite-difference gradient as scipy forms it).
+ *   par[b] = [Y (d x resolution: samples of the old spline) | b (d x 6: old position at t0, t1, velocity, acceleration)]
+ *   x: in = initial control points (tg_smooth_initial_batch: the arc-length walk of create_initial_control_points,
+ *      :83-112; scratch = B * oldN doubles), out = solution.  d * N <= 62.  Device pointers.
+ */
+size_t tg_smooth_workspace_bytes(int d, int N, int order, int resolution, int B);
+int tg_smooth_batch(int d, int N, int order, int resolution, double scale, int B, const double *par, double *x,
+                    double *f, int *status, int *nit, int maxiter, double ftol, void *workspace, size_t workspace_bytes,
+                    void *stream);
+int tg_smooth_initial_batch(int d, int oldN, int N, int B, const double *old_cps, double *x0, double *scratch, void *stream);
 
 /*
  * Problem construction on the device, device pointers:

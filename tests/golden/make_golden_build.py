@@ -55,9 +55,31 @@ def main():
             lo, hi = sfcmod.SFC(dims, T, R).getRotatedBounds()
             out["boxes"].append({"d": d, "p1": p1.flatten().tolist(), "p2": p2.flatten().tolist(), "pad": pad.tolist(),
                                  "R": R.tolist(), "lower": lo.flatten().tolist(), "upper": hi.flatten().tolist(), "length": float(Ln)})
+    # intervals per corridor chosen from the geometry (SFC_Data.__evaluate_intervals_per_corridor,
+    # DS/safe_flight_corridor.py:78-88), incl. ratios that round half to even and a single corridor
+    out["intervals"] = []
+    seqs = []
+    for d in (2, 3):
+        for ncorr in (1, 2, 3, 4, 5):
+            for _ in range(4):
+                seqs.append(np.cumsum(rng.normal(size=(d, ncorr + 1)) * rng.uniform(1, 6), 1))
+    seqs.append(np.array([[0.0, 2.0, 7.0, 10.0, 20.0], [0.0, 0.0, 0.0, 0.0, 0.0]]))          # ratios 1, 2.5, 1.5, 5
+    seqs.append(np.array([[0.0, 1.0, 4.5, 8.0], [0.0, 0.0, 0.0, 0.0], [0.0, 0.0, 0.0, 0.0]]))  # ratios 1, 3.5, 3.5
+    for seq in seqs:
+        d, ncorr = seq.shape[0], seq.shape[1] - 1
+        sfcs = []
+        for i in range(ncorr):
+            f = sfcmod.get2DRotationAndTranslationFromPoints if d == 2 else sfcmod.get3DRotationAndTranslationFromPoints
+            R, T, Ln = f(col(seq[:, i]), col(seq[:, i + 1]))
+            sfcs.append(sfcmod.SFC(col([Ln + 2.0] + [2.0] * (d - 1)), T, R))
+        for mn in (1, 2):
+            data = sfcmod.SFC_Data(tuple(sfcs), seq, mn)
+            out["intervals"].append({"d": d, "points": seq.tolist(), "min": mn,
+                                     "ipc": [int(v) for v in np.atleast_1d(data.get_intervals_per_corridor())],
+                                     "num_intervals": int(data.get_num_intervals())})
     with open(os.path.join(HERE, "build.json"), "w") as f:
         json.dump(out, f)
-    print("wrote build.json:", len(out["initial"]), "initial-variable cases,", len(out["boxes"]), "boxes")
+    print("wrote build.json:", len(out["initial"]), "initial-variable cases,", len(out["boxes"]), "boxes,", len(out["intervals"]), "interval cases")
 
 
 if __name__ == "__main__":

@@ -44,6 +44,35 @@ def main():
         tt = np.sort(rng.uniform(-0.5, scale * (cps.shape[1] - 3) + 0.5, size=40))
         rec["timedataset"] = {"time": tt.tolist(), "data": me.matrix_bspline_evaluation_for_timedataset(3, cps, tt, scale).tolist()}
         out["splines"][name] = rec
+    # other orders (get_M_matrix serves 2 .. 5; order 1 raises in the reference) and the single-point helpers
+    out["orders"] = {}
+    for order in (2, 4, 5):
+        cps = rng.normal(size=(2 + order % 2, order + 6)) * 3
+        scale = 0.6 + 0.3 * order
+        rec = {"control_points": cps.tolist(), "scale_factor": scale,
+               "dataset": me.matrix_bspline_evaluation_for_dataset(order, cps, 41).tolist(), "derivative_dataset": {}, "discrete": []}
+        for r in range(1, min(order, 3) + 1):
+            rec["derivative_dataset"][str(r)] = me.matrix_bspline_derivative_evaluation_for_dataset(order, r, scale, cps, 37).tolist()
+        for r in (0, 1):
+            if r == 0:
+                d, t, rem, end = me.matrix_bspline_evaluation_for_discrete_steps(order, cps, 0.5, 0.2, 0.3, scale)
+            else:
+                d, t, rem, end = me.matrix_bspline_derivative_evaluation_for_discrete_steps(order, r, scale, cps, 0.5, 0.2, 0.3)
+            rec["discrete"].append({"start_time": 0.5, "offset": 0.2, "dt": 0.3, "r": r, "data": d.tolist(), "time": t.tolist(),
+                                    "remainder": rem, "end": end})
+        out["orders"][str(order)] = rec
+    out["helpers"] = {"M": {str(o): me.get_M_matrix(o).tolist() for o in (2, 3, 4, 5)}, "points": []}
+    for order in (2, 3, 4, 5):
+        cp = rng.normal(size=(3, order + 1)) * 2
+        for (t, tj, sf, r) in ((1.37, 1.0, 0.8, 0), (2.5, 2.0, 1.3, 1), (0.4, 0.0, 0.5, 2)):
+            if r > order:
+                continue
+            val = (me.evaluate_point_on_interval(cp, t, tj, sf) if r == 0 else
+                   me.evaluate_point_derivative_on_interval(cp, t, tj, sf, r))
+            out["helpers"]["points"].append({"control_points": cp.tolist(), "t": t, "tj": tj, "scale": sf, "r": r,
+                                             "value": np.asarray(val).tolist(),
+                                             "T": (me.get_T_vector(order, t, tj, sf) if r == 0 else
+                                                   me.get_T_derivative_vector(order, t, tj, r, sf)).tolist()})
     conc = SplineDataConcatenater(2)
     lst = [splines[k][0] for k in ("concat1", "concat2", "concat3")]
     sc = [splines[k][1] for k in ("concat1", "concat2", "concat3")]

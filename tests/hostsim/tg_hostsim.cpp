@@ -9,6 +9,7 @@
 #include "../../trajectory_generator_b200/csrc/tg_eval.h"
 #ifdef TG_WITH_SQP
 #include "../../trajectory_generator_b200/csrc/tg_sqp.h"
+#include "../../trajectory_generator_b200/csrc/tg_smooth.h"
 #endif
 
 extern "C" int hs_layout(const int *spec, int *out, int cap)
@@ -95,3 +96,28 @@ extern "C" void hs_ldl_update(int n, double sigma, const double *z, double *Lm, 
 }
 #endif
 
+
+#ifdef TG_WITH_SQP
+// spline order converter (csrc/tg_smooth.h) on the host: table + one solve.  par = [Y | b], x in/out
+extern "C" int hs_smooth_solve(int d, int N, int order, int resolution, double scale, const double *par, double *x,
+                               double *fout, int *nit)
+{
+    const TgSmoothShape S = {d, N, order, resolution, scale};
+    std::vector<double> tab(tg_smooth_table_doubles(S));
+    for (int t = 0; t < resolution; t++) tg_smooth_table_entry(S, t, tab.data());
+    for (int q = 0; q < 6; q++) tg_smooth_end_entry(S, q, tab.data());
+    TgLayout L;
+    tg_smooth_layout(S, &L);
+    std::vector<double> ws(tg_sqp_workspace_doubles(L));
+    TgSqpResult res;
+    tg_smooth_solve(S, tab.data(), par, x, ws.data(), 100, 1e-6, &res);
+    *fout = res.f; *nit = res.nit;
+    return res.status;
+}
+
+extern "C" void hs_smooth_initial(int d, const double *old_pts, int oldN, int N, double *out)
+{
+    std::vector<double> scr(oldN);
+    tg_smooth_initial_points(d, old_pts, oldN, N, out, scr.data());
+}
+#endif

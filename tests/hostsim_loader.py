@@ -50,7 +50,7 @@ class HostSim:
 
 
 def load():
-    deps = [SRC] + [os.path.join(CSRC, f) for f in ("tg_eval.h", "tg_sqp.h", "tg_spec.h")]
+    deps = [SRC] + [os.path.join(CSRC, f) for f in ("tg_eval.h", "tg_sqp.h", "tg_spec.h", "tg_smooth.h")]
     if not os.path.exists(OUT) or any(os.path.getmtime(OUT) < os.path.getmtime(d) for d in deps):
         subprocess.run(["g++", "-std=c++14", "-O2", "-fPIC", "-shared", "-ffp-contract=off", "-Wno-unknown-pragmas",
                         "-DTG_WITH_SQP", "-o", OUT, SRC], check=True, capture_output=True)

@@ -21,6 +21,9 @@ def test_oracle_matches_reference_fixtures():
         R, lo, hi, ln = ob.box_from_points(rec["p1"], rec["p2"], rec["pad"])
         assert np.array_equal(R, np.array(rec["R"])) and np.array_equal(lo, np.array(rec["lower"]))
         assert np.array_equal(hi, np.array(rec["upper"])) and ln == rec["length"]
+    for rec in G["intervals"]:
+        assert ob.intervals_per_corridor(rec["points"], rec["min"]) == rec["ipc"]
+        assert sum(rec["ipc"]) == rec["num_intervals"]
 
 
 def _spec(d, N, niw=0, ncorr=0):
@@ -97,3 +100,81 @@ def test_cuda_builders_reproduce_the_c4_batch(native_lib):
     assert np.abs(par.cpu().numpy() - b.par).max() <= 1e-12
     x0 = builder.initial_guess_batch(b.spec, pts).cpu().numpy()
     assert np.abs(x0 - b.x0).max() <= 1e-12
+
+
+@pytest.mark.gpu
+def test_cuda_intervals_per_corridor_match_reference_fixtures(native_lib):
+    """shape from geometry (DS/safe_flight_corridor.py:78-88) on the device, incl. the round-half-to-even ratios"""
+    import torch
+    from trajectory_generator_b200 import builder
+    G = _golden()
+    groups = {}
+    for rec in G["intervals"]:
+        pts = np.array(rec["points"])
+        groups.setdefault((pts.shape, rec["min"]), []).append(rec)
+    for (shape, mn), recs in groups.items():
+        pts = torch.from_numpy(np.stack([np.array(r["points"]) for r in recs])).cuda()
+        ipc, key = builder.sfc_intervals_batch(pts, mn)
+        ipc = ipc.cpu().numpy(); key = key.cpu().numpy()
+        for i, r in enumerate(recs):
+            assert ipc[i].tolist() == r["ipc"], (shape, mn, i)
+        for i in range(len(recs)):
+            for j in range(len(recs)):
+                assert (key[i] == key[j]) == (recs[i]["ipc"] == recs[j]["ipc"])
+
+
+@pytest.mark.gpu
+def test_corridor_problems_built_from_raw_geometry(native_lib):
+    """f2 -> f3: raw corridor polylines in, shapes chosen on the device, one solve call for all shapes; every problem's
+    answer equals the one-shape-at-a-time answer of the array-level API on the same rows, and the drop-in class
+    (which lets SFC_Data choose the intervals on the host) lands on the same control points."""
+    import torch
+    from trajectory_generator_b200 import batch
+    from trajectory_generator_b200.batched import CorridorProblems
+    import helpers as h
+    rng = np.random.default_rng(12)
+    B, ncorr = 96, 3
+    pts = np.zeros((B, 3, ncorr + 1))
+    pts[:, :, 0] = rng.uniform(-5, 5, (B, 3))
+    direction = rng.normal(size=(B, 3)); direction /= np.linalg.norm(direction, 2, 1)[:, None]
+    for i in range(1, ncorr + 1):
+        turn = rng.normal(size=(B, 3)) * 0.35
+        direction = direction + turn; direction /= np.linalg.norm(direction, 2, 1)[:, None]
+        pts[:, :, i] = pts[:, :, i - 1] + direction * rng.uniform(5, 11.5, B)[:, None]
+    pads = np.stack([rng.uniform(2, 3, (B, ncorr)), rng.uniform(2, 3, (B, ncorr)), rng.uniform(2, 4, (B, ncorr))], 2)
+    v0 = pts[:, :, 1] - pts[:, :, 0]; v0 /= np.linalg.norm(v0, 2, 1)[:, None]
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    cp = CorridorProblems(3, corridor_points=t(pts), corridor_pads=t(pads), start_velocity=t(v0), end_zero_velocity=True,
+                          max_velocity=5.0, max_acceleration=0.3, objective_function_type="minimal_velocity_path")
+    shapes = cp.shapes()
+    assert len(shapes) >= 3 and sum(c for _, c in shapes) == B
+    out = cp.solve()
+    assert (out["status"] == 0).double().mean().item() > 0.9
+    seen = torch.zeros(B, dtype=torch.int32, device="cuda")
+    for idx, prob, x in out["buckets"]:
+        seen[idx] += 1
+        one = batch.solve(prob.spec, prob.par, prob.x0.clone(), jacobian="fd")
+        assert torch.equal(one["x"], x) and torch.equal(one["status"], out["status"][idx])
+    assert (seen == 1).all()
+    # the drop-in route on a few problems: containers -> SFC_Data chooses the same intervals -> same solution
+    from trajectory_generator_b200.trajectory_generator import TrajectoryGenerator
+    ns = h.product_namespace()
+    col = lambda v: np.asarray(v, dtype=float).reshape(-1, 1)
+    gen = TrajectoryGenerator(3)
+    for idx, prob, x in out["buckets"][:3]:
+        b = int(idx[0].item())
+        sfcs = []
+        for k in range(ncorr):
+            R, T, Ln = ns["get3DRotationAndTranslationFromPoints"](col(pts[b, :, k]), col(pts[b, :, k + 1]))
+            dims = pads[b, k].copy(); dims[0] += Ln
+            sfcs.append(ns["SFC"](col(dims), T, R))
+        sfc = ns["SFC_Data"](tuple(sfcs), pts[b], 1)
+        assert [int(v) for v in sfc.get_intervals_per_corridor()] == cp.ipc[b].cpu().tolist()
+        wd = ns["WaypointData"]((ns["Waypoint"](location=col(pts[b, :, 0]), velocity=col(v0[b])),
+                                 ns["Waypoint"](location=col(pts[b, :, -1]), velocity=col([0, 0, 0]))))
+        cc = ns["ConstraintsContainer"](wd, ns["DerivativeBounds"](5.0, 0.3), None, sfc, None)
+        cps, scale, viol = gen.generate_trajectory(cc, "minimal_velocity_path")
+        mine = x[0, :prob.d * prob.N].reshape(prob.d, prob.N).cpu().numpy()
+        assert cps.shape == mine.shape
+        if gen.last_result.status == 0 and int(out["status"][b].item()) == 0:
+            assert np.abs(cps - mine).max() <= 1e-4          # inputs agree to ~1e-16; forward differences amplify that

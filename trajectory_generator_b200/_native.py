@@ -26,8 +26,8 @@ LAYOUT_FIELDS = ("d N nint n ia is0 is1 it0 nws niw meq mineq m r_start n_start 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC"]
 # translation units: the host API (+ legacy single-problem kernels) and one unit per (kernel family, lanes per problem)
-UNITS = ["tg_api.cu", "tg_sample.cu", "tg_build.cu", "tg_solve_fused.cu", "tg_solve_g64.cu"] + ["tg_%s_g%d.cu" % (fam, gs) for fam in ("eval", "solve", "solve_fd") for gs in (8, 16, 32)]
-HEADERS = ["tg_sqp.h", "tg_eval.h", "tg_spec.h", "tg_shape.h", "tg_kernels_eval.inc", "tg_kernels_solve.inc"]
+UNITS = ["tg_api.cu", "tg_sample.cu", "tg_build.cu", "tg_smooth.cu", "tg_solve_fused.cu", "tg_solve_g64.cu"] + ["tg_%s_g%d.cu" % (fam, gs) for fam in ("eval", "solve", "solve_fd") for gs in (8, 16, 32)]
+HEADERS = ["tg_sqp.h", "tg_eval.h", "tg_spec.h", "tg_shape.h", "tg_smooth.h", "tg_kernels_eval.inc", "tg_kernels_solve.inc"]
 
 
 def build_native(force=False, verbose=False, variant=None, extra_flags=()):
@@ -109,6 +109,19 @@ def lib():
                                       ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, ctypes.c_double, vp, ctypes.c_long,
                                       vp, vp, vp]
         L.tg_sample_batch.restype = ctypes.c_int
+        L.tg_sample_batch_order.argtypes = [ctypes.c_int] + list(L.tg_sample_batch.argtypes)
+        L.tg_sample_batch_order.restype = ctypes.c_int
+        L.tg_interval_points_batch.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp, ctypes.c_int, vp, vp]
+        L.tg_interval_points_batch.restype = ctypes.c_int
+        L.tg_sfc_intervals_batch.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, ctypes.c_int, vp, vp, vp]
+        L.tg_sfc_intervals_batch.restype = ctypes.c_int
+        L.tg_smooth_workspace_bytes.argtypes = [ctypes.c_int] * 5
+        L.tg_smooth_workspace_bytes.restype = sz
+        L.tg_smooth_batch.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_int,
+                                      vp, vp, vp, vp, vp, ctypes.c_int, ctypes.c_double, vp, sz, vp]
+        L.tg_smooth_batch.restype = ctypes.c_int
+        L.tg_smooth_initial_batch.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp]
+        L.tg_smooth_initial_batch.restype = ctypes.c_int
         L.tg_initial_guess_batch.argtypes = [_I32, ctypes.c_int, vp, ctypes.c_int, vp, ctypes.c_int, ctypes.c_double, vp, vp]
         L.tg_initial_guess_batch.restype = ctypes.c_int
         L.tg_sfc_boxes_batch.argtypes = [_I32, ctypes.c_int, vp, vp, vp, vp, vp]

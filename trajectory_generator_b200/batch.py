@@ -102,10 +102,16 @@ def solve(spec, par, x, maxiter=100, ftol=1e-6, jacobian="analytic", buffers=Non
     if not (par.is_cuda and x.is_cuda):
         raise RuntimeError("solve() needs CUDA tensors (there is no CPU path); use solve_host for numpy input")
     B = x.shape[0]
-    assert par.is_contiguous() and x.is_contiguous()
-    assert par.shape == (B, lay.P) and x.shape == (B, lay.n)
+    if par.dtype != torch.float64 or x.dtype != torch.float64:
+        raise ValueError("solve() needs float64 tensors, got %s / %s" % (par.dtype, x.dtype))
+    if par.device != x.device:
+        raise ValueError("par and x live on different devices")
+    if not (par.is_contiguous() and x.is_contiguous()) or par.shape != (B, lay.P) or x.shape != (B, lay.n):
+        raise ValueError("par [B, %d] and x [B, %d] must be contiguous tensors of the descriptor's shape" % (lay.P, lay.n))
     dev = x.device
     buf = buffers if buffers is not None else SolveBuffers(spec, B, dev)
+    if buf.B < B or not np.array_equal(buf.spec, np.ascontiguousarray(spec, dtype=np.int32)) or buf.ws.device != dev:
+        raise ValueError("the SolveBuffers were made for another shape, a smaller batch or another device")
     with torch.cuda.device(dev):
         rc = _native.lib().tg_solve_batch(buf.sp, B, _ptr(par), _ptr(x), _ptr(buf.f), _ptr(buf.status), _ptr(buf.nit),
                                           _ptr(buf.violation), int(maxiter), float(ftol), _flags(jacobian, fused),
@@ -187,4 +193,49 @@ def solve_mixed_host(buckets, maxiter=100, ftol=1e-6, jacobian="analytic"):
     rc = L.tg_solve_mixed_host(nb, specs.ctypes.data, counts.ctypes.data, ptrs["par"], ptrs["x"], ptrs["f"], ptrs["status"],
                                ptrs["nit"], ptrs["violation"], int(maxiter), float(ftol), _flags(jacobian, False))
     _native.check(rc, "tg_solve_mixed_host")
+    return outs
+
+
+def solve_mixed(buckets, maxiter=100, ftol=1e-6, jacobian="analytic"):
+    """Device-resident M2 solve of problems of DIFFERENT shapes in one call (tg_solve_mixed_batch).
+    buckets: list of (spec, par [Bk, P], x [Bk, n]) CUDA tensors; x is overwritten with the solution.  The buckets run
+    concurrently on internal streams that fork from and join the current stream.  Returns one dict(x, f, status, nit,
+    violation) of CUDA tensors per bucket."""
+    torch = _torch()
+    L = _native.lib()
+    nb = len(buckets)
+    if nb == 0:
+        return []
+    nspec = L.tg_spec_count()
+    specs = np.zeros((nb, nspec), dtype=np.int32)
+    counts = np.zeros(nb, dtype=np.int32)
+    vp_array = ctypes.c_void_p * nb
+    ptrs = {k: vp_array() for k in ("par", "x", "f", "status", "nit", "violation")}
+    outs, keep = [], []
+    dev = buckets[0][2].device
+    for k, (spec, par, x) in enumerate(buckets):
+        lay = Layout(spec)
+        if not (par.is_cuda and x.is_cuda) or par.device != dev or x.device != dev:
+            raise RuntimeError("solve_mixed() needs CUDA tensors on one device (there is no CPU path)")
+        if par.dtype != torch.float64 or x.dtype != torch.float64:
+            raise ValueError("solve_mixed() needs float64 tensors")
+        B = x.shape[0]
+        if not (par.is_contiguous() and x.is_contiguous()) or par.shape != (B, lay.P) or x.shape != (B, lay.n):
+            raise ValueError("bucket %d: par / x do not have the shapes of the descriptor" % k)
+        specs[k] = np.ascontiguousarray(spec, dtype=np.int32)
+        counts[k] = B
+        out = dict(x=x, f=torch.empty(B, dtype=torch.float64, device=dev), status=torch.empty(B, dtype=torch.int32, device=dev),
+                   nit=torch.empty(B, dtype=torch.int32, device=dev), violation=torch.empty(B, dtype=torch.int32, device=dev))
+        outs.append(out); keep.append(par)
+        ptrs["par"][k] = par.data_ptr()
+        for name in ("x", "f", "status", "nit", "violation"):
+            ptrs[name][k] = out[name].data_ptr()
+    L.tg_solve_mixed_batch.restype = ctypes.c_int
+    L.tg_solve_mixed_batch.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_void_p] * 6 + \
+                                      [ctypes.c_int, ctypes.c_double, ctypes.c_int, ctypes.c_void_p]
+    with torch.cuda.device(dev):
+        rc = L.tg_solve_mixed_batch(nb, specs.ctypes.data, counts.ctypes.data, ptrs["par"], ptrs["x"], ptrs["f"], ptrs["status"],
+                                    ptrs["nit"], ptrs["violation"], int(maxiter), float(ftol), _flags(jacobian, False),
+                                    _stream(torch, dev))
+    _native.check(rc, "tg_solve_mixed_batch")
     return outs

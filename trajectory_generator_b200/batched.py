@@ -188,3 +188,61 @@ class BatchedProblem:
     def sample(self, out, num_points=None, dt=None, derivative_order=0):
         return matrix_evaluation.sample_batch((out["x"], self.d, self.N), derivative_order=derivative_order,
                                               num_points=num_points, dt=dt)
+
+
+class CorridorProblems:
+    """Corridor problems whose SHAPE follows from their geometry, as in the reference: ``SFC_Data`` chooses the
+    intervals of every corridor from the segment lengths (DS/safe_flight_corridor.py:78-88) and
+    ``TrajectoryGenerator`` the number of control points from their sum (TG/trajectory_generator.py:148-162), so a
+    batch of raw corridor polylines is a mix of shapes.  Everything happens on the device: intervals per corridor
+    (``tg_sfc_intervals_batch``), grouping by shape key (one sort), one ``BatchedProblem`` per shape (boxes, parameter
+    rows, initial guess), and ONE solve call for all shapes (``tg_solve_mixed_batch``).
+
+        cp = CorridorProblems(3, corridor_points=pts, corridor_pads=pads, start_velocity=v0, end_zero_velocity=True,
+                              max_velocity=5.0, max_acceleration=0.3, objective_function_type="minimal_velocity_path")
+        out = cp.solve()      # status / nit / f / violation [B] in input order; out["buckets"]: per shape (indices, problem, x)
+
+    Per-problem tensor arguments (anything with a leading batch axis) are split along with the problems; scalars and
+    tuples are shared."""
+
+    def __init__(self, dimension, corridor_points, corridor_pads, min_intervals_per_corridor=1, **fields):
+        torch = _torch()
+        if not corridor_points.is_cuda:
+            raise RuntimeError("CorridorProblems needs CUDA tensors (there is no CPU path)")
+        pts = corridor_points.to(torch.float64).contiguous()
+        B = pts.shape[0]
+        self.B, self.d = B, int(dimension)
+        self.ipc, key = builder.sfc_intervals_batch(pts, min_intervals_per_corridor)
+        uniq, inverse = torch.unique(key, return_inverse=True)
+        order = torch.argsort(inverse, stable=True)
+        counts = torch.bincount(inverse, minlength=len(uniq)).cpu().tolist()
+        self.buckets = []
+        lo = 0
+        for cnt in counts:
+            idx = order[lo:lo + cnt]
+            lo += cnt
+            take = lambda v: v[idx] if (torch.is_tensor(v) and v.dim() >= 1 and v.shape[0] == B) else v
+            sub = {k: take(v) for k, v in fields.items()}
+            ipc = self.ipc[idx[0]].cpu().tolist()
+            prob = BatchedProblem(self.d, start=pts[idx][:, :, 0].contiguous(), end=pts[idx][:, :, -1].contiguous(),
+                                  corridor_points=pts[idx].contiguous(), corridor_pads=corridor_pads[idx].contiguous(),
+                                  intervals_per_corridor=ipc, **sub)
+            self.buckets.append((idx, prob))
+
+    def shapes(self):
+        """-> list of (intervals per corridor, number of problems), one entry per shape"""
+        return [(self.ipc[idx[0]].cpu().tolist(), int(idx.numel())) for idx, _ in self.buckets]
+
+    def solve(self, jacobian="fd", maxiter=100, ftol=1e-6):
+        torch = _torch()
+        xs = [p.x0.clone() for _, p in self.buckets]
+        outs = tgb.solve_mixed([(p.spec, p.par, x) for (_, p), x in zip(self.buckets, xs)], maxiter, ftol, jacobian)
+        dev = xs[0].device
+        res = dict(status=torch.empty(self.B, dtype=torch.int32, device=dev), nit=torch.empty(self.B, dtype=torch.int32, device=dev),
+                   violation=torch.empty(self.B, dtype=torch.int32, device=dev), f=torch.empty(self.B, dtype=torch.float64, device=dev),
+                   buckets=[])
+        for (idx, prob), out in zip(self.buckets, outs):
+            for k in ("status", "nit", "violation", "f"):
+                res[k][idx] = out[k]
+            res["buckets"].append((idx, prob, out["x"]))
+        return res

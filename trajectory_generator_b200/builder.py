@@ -63,3 +63,20 @@ def sfc_boxes_batch(spec, points, pads, par):
                                               ctypes.c_void_p(torch.cuda.current_stream(points.device).cuda_stream))
     _native.check(rc, "tg_sfc_boxes_batch")
     return lengths
+
+
+def sfc_intervals_batch(points, min_intervals_per_corridor=1):
+    """points [B, d, ncorr + 1] (CUDA): intervals per corridor as the reference's SFC_Data chooses them from the geometry
+    (DS/safe_flight_corridor.py:78-88).  Returns (ipc [B, ncorr] int32, key [B] int64: equal for problems of one shape)."""
+    torch = _torch()
+    points = points.contiguous()
+    if not points.is_cuda:
+        raise RuntimeError("sfc_intervals_batch() needs CUDA tensors (there is no CPU path)")
+    B, d, np1 = points.shape
+    ipc = torch.empty((B, np1 - 1), dtype=torch.int32, device=points.device)
+    key = torch.empty(B, dtype=torch.int64, device=points.device)
+    with torch.cuda.device(points.device):
+        rc = _native.lib().tg_sfc_intervals_batch(d, np1 - 1, B, _ptr(points), int(min_intervals_per_corridor), _ptr(ipc), _ptr(key),
+                                                  ctypes.c_void_p(torch.cuda.current_stream(points.device).cuda_stream))
+    _native.check(rc, "tg_sfc_intervals_batch")
+    return ipc, key

@@ -630,12 +630,14 @@ struct TgMixedCtx {
 };
 static TgMixedCtx g_mixed_ctx[TG_MAX_DEVICES];
 
-extern "C" int tg_solve_mixed_host(int nbuckets, const int *specs, const int *counts, const double *const *par,
-                                   double *const *x, double *const *f, int *const *status, int *const *nit,
-                                   int *const *violation, int maxiter, double ftol, int flags)
+// shared by tg_solve_mixed_host (host buffers: copies on the bucket's stream) and tg_solve_mixed_batch (device
+// pointers: the buckets' streams fork from and join the caller's stream)
+static int tg_solve_mixed_impl(bool host, int nbuckets, const int *specs, const int *counts, const double *const *par,
+                               double *const *x, double *const *f, int *const *status, int *const *nit,
+                               int *const *violation, int maxiter, double ftol, int flags, cudaStream_t caller)
 {
     if (nbuckets <= 0) return 0;
-    if (!specs || !counts || !par || !x) return tg_fail(1, "tg_solve_mixed_host: NULL argument");
+    if (!specs || !counts || !par || !x) return tg_fail(1, "tg_solve_mixed: NULL argument");
     int rc = tg_device_check();
     if (rc) return rc;
     int dev = 0;
@@ -647,11 +649,17 @@ extern "C" int tg_solve_mixed_host(int nbuckets, const int *specs, const int *co
     for (int k = 0; k < nbuckets; k++) {
         TgShape S;
         if ((rc = tg_make_shape(specs + (size_t)k * TG_SP_COUNT, &S))) return rc;
-        if (counts[k] > 0 && (!par[k] || !x[k])) return tg_fail(1, "tg_solve_mixed_host: NULL bucket buffer");
+        if (counts[k] > 0 && (!par[k] || !x[k])) return tg_fail(1, "tg_solve_mixed: NULL bucket buffer");
     }
     const int workers = nbuckets < TG_MIXED_WORKERS ? nbuckets : TG_MIXED_WORKERS;
     for (int w = 0; w < workers; w++)
         if (!g_mixed[w].st) TG_CUDA(cudaStreamCreateWithFlags(&g_mixed[w].st, cudaStreamNonBlocking));
+    cudaEvent_t fork = nullptr;
+    if (!host) {
+        TG_CUDA(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
+        TG_CUDA(cudaEventRecord(fork, caller));
+        for (int w = 0; w < workers; w++) TG_CUDA(cudaStreamWaitEvent(g_mixed[w].st, fork, 0));
+    }
     // largest buckets first: the long solves start early and the small ones fill in around them
     std::vector<int> order(nbuckets);
     for (int k = 0; k < nbuckets; k++) order[k] = k;
@@ -675,27 +683,36 @@ extern "C" int tg_solve_mixed_host(int nbuckets, const int *specs, const int *co
             const size_t nb = sizeof(double);
             const size_t wsb = tg_solve_workspace_bytes(spec, B);
             int r = wsb ? 0 : tg_fail(5, g_err[0] ? g_err : "cannot plan the solve kernel");
-            if (!r) r = s.par.ensure((size_t)B * (L.P + 1) * nb);
-            if (!r) r = s.x.ensure((size_t)B * L.n * nb);
-            if (!r) r = s.f.ensure((size_t)B * nb);
-            if (!r) r = s.i.ensure((size_t)B * 3 * sizeof(int));
             if (!r) r = s.ws.ensure(wsb);
+            if (host) {
+                if (!r) r = s.par.ensure((size_t)B * (L.P + 1) * nb);
+                if (!r) r = s.x.ensure((size_t)B * L.n * nb);
+                if (!r) r = s.f.ensure((size_t)B * nb);
+                if (!r) r = s.i.ensure((size_t)B * 3 * sizeof(int));
+            }
             int *di = (int *)s.i.p;
             auto cp = [&](void *dst, const void *src, size_t bytes, cudaMemcpyKind kind) {
                 if (r) return;
                 cudaError_t e = cudaMemcpyAsync(dst, src, bytes, kind, s.st);
                 if (e != cudaSuccess) r = tg_fail(100 + (int)e, "cudaMemcpyAsync", e);
             };
-            cp(s.par.p, par[k], (size_t)B * L.P * nb, cudaMemcpyHostToDevice);
-            cp(s.x.p, x[k], (size_t)B * L.n * nb, cudaMemcpyHostToDevice);
-            if (!r) r = tg_solve_batch(spec, B, (const double *)s.par.p, (double *)s.x.p, (double *)s.f.p, di, di + B, di + 2 * B,
-                                       maxiter, ftol, flags, s.ws.p, wsb, s.st);
-            cp(x[k], s.x.p, (size_t)B * L.n * nb, cudaMemcpyDeviceToHost);
-            if (f && f[k]) cp(f[k], s.f.p, (size_t)B * nb, cudaMemcpyDeviceToHost);
-            if (status && status[k]) cp(status[k], di, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost);
-            if (nit && nit[k]) cp(nit[k], di + B, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost);
-            if (violation && violation[k]) cp(violation[k], di + 2 * B, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost);
-            cudaError_t e = cudaStreamSynchronize(s.st);
+            if (host) {
+                cp(s.par.p, par[k], (size_t)B * L.P * nb, cudaMemcpyHostToDevice);
+                cp(s.x.p, x[k], (size_t)B * L.n * nb, cudaMemcpyHostToDevice);
+                if (!r) r = tg_solve_batch(spec, B, (const double *)s.par.p, (double *)s.x.p, (double *)s.f.p, di, di + B, di + 2 * B,
+                                           maxiter, ftol, flags, s.ws.p, wsb, s.st);
+                cp(x[k], s.x.p, (size_t)B * L.n * nb, cudaMemcpyDeviceToHost);
+                if (f && f[k]) cp(f[k], s.f.p, (size_t)B * nb, cudaMemcpyDeviceToHost);
+                if (status && status[k]) cp(status[k], di, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost);
+                if (nit && nit[k]) cp(nit[k], di + B, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost);
+                if (violation && violation[k]) cp(violation[k], di + 2 * B, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost);
+            } else if (!r) {
+                r = tg_solve_batch(spec, B, par[k], x[k], f ? f[k] : nullptr, status ? status[k] : nullptr, nit ? nit[k] : nullptr,
+                                   violation ? violation[k] : nullptr, maxiter, ftol, flags, s.ws.p, wsb, s.st);
+            }
+            // (the slot's workspace and staging buffers are reused by this worker's next bucket, which is queued on the
+            // same stream; host buffers must be complete before the call returns)
+            cudaError_t e = host ? cudaStreamSynchronize(s.st) : cudaSuccess;
             if (!r && e != cudaSuccess) r = tg_fail(100 + (int)e, "cudaStreamSynchronize", e);
             if (r) { rcs[w] = r; errs[w] = g_err; break; }
         }
@@ -704,9 +721,32 @@ extern "C" int tg_solve_mixed_host(int nbuckets, const int *specs, const int *co
     for (int w = 1; w < workers; w++) pool.emplace_back(work, w);
     work(0);
     for (std::thread &t : pool) t.join();
+    if (!host) {
+        // the caller's stream continues after every bucket's stream
+        for (int w = 0; w < workers; w++) {
+            cudaEventRecord(fork, g_mixed[w].st);
+            cudaStreamWaitEvent(caller, fork, 0);
+        }
+        cudaEventDestroy(fork);
+    }
     for (int w = 0; w < workers; w++)
         if (rcs[w]) return tg_fail(rcs[w], errs[w].c_str());
     return 0;
+}
+
+extern "C" int tg_solve_mixed_host(int nbuckets, const int *specs, const int *counts, const double *const *par,
+                                   double *const *x, double *const *f, int *const *status, int *const *nit,
+                                   int *const *violation, int maxiter, double ftol, int flags)
+{
+    return tg_solve_mixed_impl(true, nbuckets, specs, counts, par, x, f, status, nit, violation, maxiter, ftol, flags, nullptr);
+}
+
+extern "C" int tg_solve_mixed_batch(int nbuckets, const int *specs, const int *counts, const double *const *par,
+                                    double *const *x, double *const *f, int *const *status, int *const *nit,
+                                    int *const *violation, int maxiter, double ftol, int flags, void *stream)
+{
+    return tg_solve_mixed_impl(false, nbuckets, specs, counts, par, x, f, status, nit, violation, maxiter, ftol, flags,
+                               (cudaStream_t)stream);
 }
 
 // ---------------------------------------------------------------------------

@@ -147,7 +147,49 @@ tg_sfc_boxes_kernel(int d, int B, int ncorr, const double *__restrict__ points, 
     }
 }
 
+// SFC_Data.__evaluate_intervals_per_corridor (DS/safe_flight_corridor.py:78-88): the shape of a corridor problem
+// follows from its geometry -- intervals of corridor i = (int(round(length_i / shortest length)) + 1) * minimum, a
+// single corridor gets 5.  ipc[b][ncorr]; key[b] packs them (4 bits each... 8 bits each) so that problems of one
+// shape compare equal; numpy's round is round-half-to-even = rint.
+__global__ void __launch_bounds__(128)
+tg_sfc_intervals_kernel(int d, int B, int ncorr, const double *__restrict__ points, int min_per_corridor,
+                        int *__restrict__ ipc, long long *__restrict__ key)
+{
+    for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < B; b += gridDim.x * blockDim.x) {
+        const double *p = points + (size_t)b * d * (ncorr + 1);
+        double len[TG_MAX_CORRIDORS], shortest = INFINITY;
+        for (int q = 0; q < ncorr; q++) {
+            double s = 0;
+            for (int c = 0; c < d; c++) { const double v = p[c * (ncorr + 1) + q + 1] - p[c * (ncorr + 1) + q]; s += v * v; }
+            len[q] = sqrt(s);
+            shortest = fmin(shortest, len[q]);
+        }
+        long long k = 0;
+        for (int q = 0; q < ncorr; q++) {
+            const int n = ncorr < 2 ? 5 : ((int)rint(len[q] / shortest) + 1) * min_per_corridor;
+            ipc[(size_t)b * ncorr + q] = n;
+            k = (k << 8) | (long long)(n & 0xff);
+        }
+        if (key) key[b] = k;
+    }
+}
+
 }  // namespace
+
+extern "C" int tg_sfc_intervals_batch(int d, int ncorr, int B, const double *points, int min_per_corridor, int *ipc,
+                                      long long *key, void *stream)
+{
+    if (B <= 0) return 0;
+    int rc = tg_device_check();
+    if (rc) return rc;
+    if ((d != 2 && d != 3) || ncorr < 1 || ncorr > TG_MAX_CORRIDORS || !points || !ipc || min_per_corridor < 1) return 2;
+    int grid = (B + 127) / 128;
+    if (grid > 148 * 16) grid = 148 * 16;
+    tg_sfc_intervals_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(d, B, ncorr, points, min_per_corridor, ipc, key);
+    tg_note_launch(1);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : 100 + (int)e;
+}
 
 extern "C" int tg_initial_guess_batch(const int *spec, int B, const double *seq, int npts, const double *wseq, int nwp,
                                       double scale0, double *x0, void *stream)

@@ -34,25 +34,43 @@ struct SampleArgs {
     int *counts;                               // mode 1: samples of trajectory b
 };
 
-// M of TG/matrix_evaluation.py:245-250 ( /12 applied element-wise as numpy does)
-__device__ __forceinline__ double m3(int l, int col)
+// basis matrices of TG/matrix_evaluation.py:224-262 (orders 2 .. 5; the scalar factor applied element-wise as numpy does)
+template <int ORD>
+__device__ __forceinline__ double mk(int l, int col)
 {
-    const double M[4][4] = {{-2.0, 6.0, -6.0, 2.0}, {6.0, -12.0, 0.0, 8.0}, {-6.0, 6.0, 6.0, 2.0}, {2.0, 0.0, 0.0, 0.0}};
-    return M[l][col] / 12.0;
+    if (ORD == 2) {
+        const double M[3][3] = {{1.0, -2.0, 1.0}, {-2.0, 2.0, 1.0}, {1.0, 0.0, 0.0}};
+        return 0.5 * M[l][col];
+    } else if (ORD == 3) {
+        const double M[4][4] = {{-2.0, 6.0, -6.0, 2.0}, {6.0, -12.0, 0.0, 8.0}, {-6.0, 6.0, 6.0, 2.0}, {2.0, 0.0, 0.0, 0.0}};
+        return M[l][col] / 12.0;
+    } else if (ORD == 4) {
+        const double M[5][5] = {{1.0, -4.0, 6.0, -4.0, 1.0}, {-4.0, 12.0, -6.0, -12.0, 11.0}, {6.0, -12.0, -6.0, 12.0, 11.0},
+                                {-4.0, 4.0, 6.0, 4.0, 1.0}, {1.0, 0.0, 0.0, 0.0, 0.0}};
+        return M[l][col] / 24.0;
+    } else {
+        const double M[6][6] = {{-1.0, 5.0, -10.0, 10.0, -5.0, 1.0}, {5.0, -20.0, 20.0, 20.0, -50.0, 26.0},
+                                {-10.0, 30.0, 0.0, -60.0, 0.0, 66.0}, {10.0, -20.0, -20.0, 20.0, 50.0, 26.0},
+                                {-5.0, 5.0, 10.0, 10.0, 5.0, 1.0}, {1.0, 0.0, 0.0, 0.0, 0.0, 0.0}};
+        return M[l][col] / 120.0;
+    }
 }
 
 __device__ __forceinline__ double ipow(double x, int e)
 {
-    // numpy's steps_array ** e for e = 0..3 (pow() is exact for e <= 1 and within an ulp of these products)
-    return e == 0 ? 1.0 : e == 1 ? x : e == 2 ? x * x : x * x * x;
+    // numpy's steps_array ** e for e = 0..5 (pow() is exact for e <= 1 and within an ulp of these products)
+    double r = 1.0;
+#pragma unroll
+    for (int q = 0; q < 5; q++) if (q < e) r = q == 0 ? x : r * x;
+    return r;
 }
 
 // one sample: trajectory b (control points P, scale sf, derivative weights kd), sample index k
-template <int MODE, int RTH, int D>
-__device__ __forceinline__ void tg_sample_one(const SampleArgs &a, int b, int k, const double *P, double sf, const double kd[4],
+template <int MODE, int RTH, int D, int ORD>
+__device__ __forceinline__ void tg_sample_one(const SampleArgs &a, int b, int k, const double *P, double sf, const double kd[ORD + 1],
                                               int num, double step, double off, double last)
 {
-    const int nint = a.N - 3, div = num - 1;
+    const int nint = a.N - ORD, div = num - 1;
     constexpr int d = D;
     const long per = (long)a.cap;
     double t;            // sample time in units of intervals
@@ -74,24 +92,33 @@ __device__ __forceinline__ void tg_sample_one(const SampleArgs &a, int b, int k,
     const double tau = t - (double)i;
     // weights of the four control points: M (K L_r)  (TG/matrix_evaluation.py:26-29, 127-130 with the products
     // associated as P (M L); the reference forms (P M) L -- the same sums up to the last place)
-    double wl[4], w[4];
+    double wl[ORD + 1], w[ORD + 1];
 #pragma unroll
-    for (int col = 0; col < 4; col++) w[col] = col <= 3 - RTH ? (RTH == 0 ? ipow(tau, 3 - col) : kd[col] * ipow(tau, 3 - RTH - col < 0 ? 0 : 3 - RTH - col)) : 0.0;
+    for (int col = 0; col <= ORD; col++)
+        w[col] = col <= ORD - RTH ? (RTH == 0 ? ipow(tau, ORD - col) : kd[col] * ipow(tau, ORD - RTH - col < 0 ? 0 : ORD - RTH - col)) : 0.0;
 #pragma unroll
-    for (int l = 0; l < 4; l++) wl[l] = ((m3(l, 0) * w[0] + m3(l, 1) * w[1]) + m3(l, 2) * w[2]) + m3(l, 3) * w[3];
+    for (int l = 0; l <= ORD; l++) {
+        double h = mk<ORD>(l, 0) * w[0];
+#pragma unroll
+        for (int col = 1; col <= ORD; col++) h = h + mk<ORD>(l, col) * w[col];
+        wl[l] = h;
+    }
 #pragma unroll
     for (int c = 0; c < d; c++) {
         const double *p = P + c * a.N + i;
-        o[(long)c * per] = ((p[0] * wl[0] + p[1] * wl[1]) + p[2] * wl[2]) + p[3] * wl[3];
+        double h = p[0] * wl[0];
+#pragma unroll
+        for (int l = 1; l <= ORD; l++) h = h + p[l] * wl[l];
+        o[(long)c * per] = h;
     }
 }
 
 // Work item = (trajectory, chunk of 256 consecutive samples), handed to warps in a grid-stride loop: no block-level
 // synchronisation, the per-trajectory set-up is shared by 8 samples per lane, coalesced 8-byte stores per coordinate row.
-template <int MODE, int RTH, int D>
+template <int MODE, int RTH, int D, int ORD>
 __global__ void __launch_bounds__(256) tg_sample_kernel(const SampleArgs a)
 {
-    const int nint = a.N - 3;
+    const int nint = a.N - ORD;
     const int lane = threadIdx.x & 31;
     const int chunks = (int)((a.cap + 255) / 256);
     const long items = (long)a.B * chunks;
@@ -100,16 +127,16 @@ __global__ void __launch_bounds__(256) tg_sample_kernel(const SampleArgs a)
         const int b = (int)((unsigned)item / (unsigned)chunks), k0 = (int)(item - (long)b * chunks) * 256;
         const double *P = a.cps + (long)b * a.cps_stride;
         const double sf = a.scale ? a.scale[(long)b * a.scale_stride] : 1.0;
-        // (K L_r)[col] = (3-col)! / (3-r-col)! / sf^r * tau^(3-r-col), col <= 3 - r   (TG/matrix_evaluation.py:175-180)
-        double kd[4];
+        // (K L_r)[col] = (p-col)! / (p-r-col)! / sf^r * tau^(p-r-col), col <= p - r, p = order   (TG/matrix_evaluation.py:175-180)
+        double kd[ORD + 1];
         {
             const double sr = RTH == 0 ? 1.0 : RTH == 1 ? sf : RTH == 2 ? sf * sf : sf * sf * sf;
 #pragma unroll
-            for (int col = 0; col < 4; col++) {
+            for (int col = 0; col <= ORD; col++) {
                 double fac = 1.0;
 #pragma unroll
-                for (int q = 0; q < RTH; q++) fac *= (double)(3 - col - q);
-                kd[col] = col <= 3 - RTH ? (RTH == 0 ? 1.0 : fac / sr) : 0.0;
+                for (int q = 0; q < RTH; q++) fac *= (double)(ORD - col - q);
+                kd[col] = col <= ORD - RTH ? (RTH == 0 ? 1.0 : fac / sr) : 0.0;
             }
         }
         int num = a.num_points;
@@ -124,42 +151,113 @@ __global__ void __launch_bounds__(256) tg_sample_kernel(const SampleArgs a)
         }
         const int kend = num < a.cap ? num : (int)a.cap;
 #pragma unroll 2
-        for (int k = k0 + lane; k < k0 + 256 && k < kend; k += 32) tg_sample_one<MODE, RTH, D>(a, b, k, P, sf, kd, num, step, off, last);
+        for (int k = k0 + lane; k < k0 + 256 && k < kend; k += 32) tg_sample_one<MODE, RTH, D, ORD>(a, b, k, P, sf, kd, num, step, off, last);
+    }
+}
+
+
+// One point of one interval per item (TG/matrix_evaluation.py:183-222: evaluate_point_on_interval /
+// evaluate_point_derivative_on_interval): out[b][c] = cps[b][c][0 .. p] . M . T with
+// T[i] = (t - tj)^(p-r-i) / sf^(p-i) * (p-i)! / (p-i-r)!   (r = 0: ((t - tj) / sf)^(p-i)).
+template <int ORD>
+__global__ void tg_interval_point_kernel(int d, int B, const double *cps, const double *t, const double *tj, const double *sf,
+                                         int rth, double *out)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const double dtv = t[b] - tj[b], s = sf[b];
+    double T[ORD + 1];
+#pragma unroll
+    for (int i = 0; i <= ORD; i++) {
+        if (rth == 0) T[i] = pow(dtv / s, (double)(ORD - i));
+        else if (i <= ORD - rth) {
+            double fa = 1.0;
+            for (int q = 0; q < rth; q++) fa *= (double)(ORD - i - q);
+            T[i] = pow(dtv, (double)(ORD - rth - i)) / pow(s, (double)(ORD - i)) * fa;
+        } else T[i] = 0.0;
+    }
+    for (int c = 0; c < d; c++) {
+        const double *p = cps + ((long)b * d + c) * (ORD + 1);
+        double pm[ORD + 1];
+#pragma unroll
+        for (int col = 0; col <= ORD; col++) {
+            double h = p[0] * mk<ORD>(0, col);
+#pragma unroll
+            for (int l = 1; l <= ORD; l++) h = h + p[l] * mk<ORD>(l, col);
+            pm[col] = h;
+        }
+        double h = pm[0] * T[0];
+#pragma unroll
+        for (int col = 1; col <= ORD; col++) h = h + pm[col] * T[col];
+        out[(long)b * d + c] = h;
     }
 }
 
 }  // namespace
 
-extern "C" int tg_sample_batch(int d, int N, int B, const double *cps, long cps_stride, const double *scale,
-                               long scale_stride, int derivative_order, int mode, int num_points, const double *offset,
-                               double dt, double *out, long capacity, double *times, int *counts, void *stream)
+extern "C" int tg_interval_points_batch(int order, int d, int B, const double *cps, const double *t, const double *tj,
+                                        const double *scale, int derivative_order, double *out, void *stream)
 {
     if (B <= 0) return 0;
     int rc = tg_device_check();
     if (rc) return rc;
-    if ((d != 2 && d != 3) || N < 4 || derivative_order < 0 || derivative_order > 3 || capacity < 1 || !cps || !out ||
+    if (order < 2 || order > 5 || d < 1 || derivative_order < 0 || !cps || !t || !tj || !scale || !out) return 2;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int blocks = (B + 127) / 128;
+    if (order == 2) tg_interval_point_kernel<2><<<blocks, 128, 0, st>>>(d, B, cps, t, tj, scale, derivative_order, out);
+    else if (order == 3) tg_interval_point_kernel<3><<<blocks, 128, 0, st>>>(d, B, cps, t, tj, scale, derivative_order, out);
+    else if (order == 4) tg_interval_point_kernel<4><<<blocks, 128, 0, st>>>(d, B, cps, t, tj, scale, derivative_order, out);
+    else tg_interval_point_kernel<5><<<blocks, 128, 0, st>>>(d, B, cps, t, tj, scale, derivative_order, out);
+    tg_note_launch(1);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : 100 + (int)e;
+}
+
+extern "C" int tg_sample_batch_order(int order, int d, int N, int B, const double *cps, long cps_stride, const double *scale,
+                                     long scale_stride, int derivative_order, int mode, int num_points, const double *offset,
+                                     double dt, double *out, long capacity, double *times, int *counts, void *stream)
+{
+    if (B <= 0) return 0;
+    int rc = tg_device_check();
+    if (rc) return rc;
+    if (order < 2 || order > 5 || (d != 2 && d != 3) || N < order + 1 || derivative_order < 0 || derivative_order > 3 ||
+        derivative_order > order || capacity < 1 || !cps || !out ||
         (mode == 0 && (num_points < 1 || num_points > capacity)) || (mode == 1 && !(dt > 0)) || (mode != 0 && mode != 1))
         return 2;
-    const double step0 = (mode == 0 && num_points > 1) ? (double)(N - 3) / (double)(num_points - 1) : 0.0;
+    const double step0 = (mode == 0 && num_points > 1) ? (double)(N - order) / (double)(num_points - 1) : 0.0;
     SampleArgs a = {d, N, B, cps, cps_stride, scale, scale_stride, derivative_order, mode, num_points, step0, offset, dt,
                     out, capacity, times, counts};
 
-    int sms = 148;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+    int sms = 148, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const long items = (long)B * ((capacity + 255) / 256);
     if (items > 0x7fffffffL) return 2;
     long blocks = (items + 7) / 8;
     if (blocks > (long)sms * 8) blocks = (long)sms * 8;
     cudaStream_t st = (cudaStream_t)stream;
-#define TG_SAMPLE_LAUNCH(M, R)                                                                                       \
-    do { if (d == 2) tg_sample_kernel<M, R, 2><<<(int)blocks, 256, 0, st>>>(a); else tg_sample_kernel<M, R, 3><<<(int)blocks, 256, 0, st>>>(a); } while (0)
+#define TG_SAMPLE_LAUNCH(M, R, O)                                                                                    \
+    do { if (d == 2) tg_sample_kernel<M, R, 2, O><<<(int)blocks, 256, 0, st>>>(a); else tg_sample_kernel<M, R, 3, O><<<(int)blocks, 256, 0, st>>>(a); } while (0)
+#define TG_SAMPLE_RTH(M, O)                                                                                          \
+    do {                                                                                                             \
+        if (derivative_order == 0) TG_SAMPLE_LAUNCH(M, 0, O); else if (derivative_order == 1) TG_SAMPLE_LAUNCH(M, 1, O); \
+        else if (derivative_order == 2) TG_SAMPLE_LAUNCH(M, 2, O); else TG_SAMPLE_LAUNCH(M, 3, O);                   \
+    } while (0)
 #define TG_SAMPLE_MODE(M)                                                                                            \
     do {                                                                                                             \
-        if (derivative_order == 0) TG_SAMPLE_LAUNCH(M, 0); else if (derivative_order == 1) TG_SAMPLE_LAUNCH(M, 1);   \
-        else if (derivative_order == 2) TG_SAMPLE_LAUNCH(M, 2); else TG_SAMPLE_LAUNCH(M, 3);                         \
+        if (order == 3) TG_SAMPLE_RTH(M, 3); else if (order == 2) TG_SAMPLE_RTH(M, 2);                               \
+        else if (order == 4) TG_SAMPLE_RTH(M, 4); else TG_SAMPLE_RTH(M, 5);                                          \
     } while (0)
     if (mode == 0) TG_SAMPLE_MODE(0); else TG_SAMPLE_MODE(1);
     tg_note_launch(1);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? 0 : 100 + (int)e;
+}
+
+extern "C" int tg_sample_batch(int d, int N, int B, const double *cps, long cps_stride, const double *scale,
+                               long scale_stride, int derivative_order, int mode, int num_points, const double *offset,
+                               double dt, double *out, long capacity, double *times, int *counts, void *stream)
+{
+    return tg_sample_batch_order(3, d, N, B, cps, cps_stride, scale, scale_stride, derivative_order, mode, num_points, offset,
+                                 dt, out, capacity, times, counts, stream);
 }

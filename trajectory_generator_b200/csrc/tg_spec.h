@@ -12,8 +12,10 @@
 
 #if defined(__CUDACC__)
 #define TG_HD __host__ __device__ __forceinline__
+#define TG_MEMBER __host__ __device__ __forceinline__       // member functions (no `static`)
 #else
 #define TG_HD static inline
+#define TG_MEMBER inline
 #endif
 
 #define TG_MAX_CORRIDORS 8

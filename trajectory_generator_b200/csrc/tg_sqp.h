@@ -790,32 +790,22 @@ TG_FN void tg_sqp_begin(const TgLayout &L, const TgSqpWs &W, const double *xin, 
     TG_SYNC();
 }
 
-template <int D>
-TG_FN void tg_sqp_stage_ls(const TgLayout &L, const int *sp, const double *par, const TgSqpWs &W, double *trace,
-                           int trace_cap)
+// The stage is written against an evaluator `ev` -- ev.init(W): constant rows of A and whatever the QP stage needs
+// once; ev.value(W): objective at W.x (return value) and constraint rows into W.c -- so that other problem kinds
+// (the spline order converter, tg_smooth.cu) run the same line search; the trajectory evaluator is TgTrajectoryEval.
+template <class Ev>
+TG_HD void tg_sqp_stage_ls_t(const TgLayout &L, const TgSqpWs &W, const Ev &ev, double *trace, int trace_cap)
 {
     const int lane = TG_LANE(), n = L.n, meq = L.meq;
     TgSqpCtl ctl = *W.ctl;
-    const bool fd = (ctl.flags & TG_SQP_FD_JACOBIAN) != 0;
     const bool init = ctl.state == TG_ST_INIT;
     if (init || ctl.state == TG_ST_LS) {
-        if (init) {
-            TgJac sink = {W.A, 1, W.lda, 2};
-            tg_linear_jacobian_d<D>(L, sp, par, sink);
-            // rotation of the corridor that owns each interval, for the QP stage's violation scans
-            if (L.n_sfc) {
-                #pragma unroll 1
-                for (int q = lane; q < L.nint * D * D; q += TG_NL) {
-                    const int j = q / (D * D);
-                    W.rot[q] = par[L.p_sfc + tg_corridor_of_interval(sp, j) * tg_sfc_stride(D) + (q - j * D * D)];
-                }
-            }
-        }
+        if (init) ev.init(W);
         // one evaluation at the starting point, or the whole line search on the L1 merit function
         double f;
         #pragma unroll 1
         for (;;) {
-            f = tg_sqp_evaluate<D>(L, sp, par, W, false);
+            f = ev.value(W);
             ctl.nfev++;
             if (init) break;
             const double t = f + tg_violation(W, meq, W.mu);
@@ -849,6 +839,35 @@ TG_FN void tg_sqp_stage_ls(const TgLayout &L, const int *sp, const double *par, 
     TG_SYNC();
     if (lane == 0) *W.ctl = ctl;
     TG_SYNC();
+}
+
+template <int D>
+struct TgTrajectoryEval {
+    const TgLayout &L;
+    const int *sp;
+    const double *par;
+    TG_MEMBER void init(const TgSqpWs &W) const
+    {
+        TgJac sink = {W.A, 1, W.lda, 2};
+        tg_linear_jacobian_d<D>(L, sp, par, sink);
+        // rotation of the corridor that owns each interval, for the QP stage's violation scans
+        if (L.n_sfc) {
+            #pragma unroll 1
+            for (int q = TG_LANE(); q < L.nint * D * D; q += TG_NL) {
+                const int j = q / (D * D);
+                W.rot[q] = par[L.p_sfc + tg_corridor_of_interval(sp, j) * tg_sfc_stride(D) + (q - j * D * D)];
+            }
+        }
+    }
+    TG_MEMBER double value(const TgSqpWs &W) const { return tg_sqp_evaluate<D>(L, sp, par, W, false); }
+};
+
+template <int D>
+TG_FN void tg_sqp_stage_ls(const TgLayout &L, const int *sp, const double *par, const TgSqpWs &W, double *trace,
+                           int trace_cap)
+{
+    const TgTrajectoryEval<D> ev = {L, sp, par};
+    tg_sqp_stage_ls_t(L, W, ev, trace, trace_cap);
 }
 
 // stage DER: derivatives at the point stage LS accepted -- the analytic gradient and Jacobian rows (values are
