@@ -400,20 +400,22 @@ def bench_config(G, name, B, steps, warmup, full=True):
                            "traffic": None, "peak_source": peak_src}
 
     # ---- e2e: host buffers through the C-ABI (tg_solve_host), copies inside the timed call
-    x_host = bt.x0.copy()
+    par_pin = tgb.pinned_empty(bt.par.shape); par_pin[:] = bt.par
+    x_pin = tgb.pinned_empty(bt.x0.shape)
     e2e_times = []
     for it in range(1 + min(steps, 2)):
-        x_host[:] = bt.x0
+        x_pin[:] = bt.x0
         G.barrier()
         t = time.perf_counter()
-        tgb.solve_host(bt.spec, bt.par, x_host, jacobian=args.jacobian, fused=args.fused)
+        tgb.solve_host(bt.spec, par_pin, x_pin, jacobian=args.jacobian, fused=args.fused)
         G.barrier()
         if it > 0:
             e2e_times.append(time.perf_counter() - t)
+    del par_pin, x_pin
     e2e_s = G.max_over_ranks(float(np.mean(e2e_times)))
     rec["e2e"] = {"value": G.world * B / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 8 * B * (L.P + L.n),
                   "d2h_bytes_per_step": 8 * B * (L.n + 1) + 4 * B * 3,
-                  "api": "tg_solve_host (C-ABI, host buffers; copies inside the call)"}
+                  "api": "tg_solve_host (C-ABI, page-locked host buffers; copies inside the call)"}
     if not full:
         return rec, arrays
 
@@ -431,20 +433,27 @@ def bench_config(G, name, B, steps, warmup, full=True):
     ev_out = {}
     ms_eval = G.timed(lambda: tgb.evaluate(bt.spec, par, xe, out=ev_out), steps, warmup)
     eval_bytes = 8 * (L.n + L.P + L.m + L.m_nl * L.n + 1 + L.n)
+    # e2e: host buffers through tg_eval_host -- page-locked buffers (as the contract asks), reused between calls; the
+    # library pipelines the batch in chunks (upload / kernel / download overlap)
+    hp = {"par": tgb.pinned_empty(bt.par.shape), "x": tgb.pinned_empty(xe_h.shape)}
+    hp["par"][:] = bt.par; hp["x"][:] = xe_h
+    hout = {k: tgb.pinned_empty(shp) for k, shp in (("f", (B,)), ("g", (B, L.n)), ("c", (B, L.m)), ("jnl", (B, L.m_nl, L.n)))}
     te = []
-    for it in range(3):
+    for it in range(4):
         G.barrier()
         t = time.perf_counter()
-        tgb.evaluate_host(bt.spec, bt.par, xe_h)
+        tgb.evaluate_host(bt.spec, hp["par"], hp["x"], out=hout)
         if it > 0:
             te.append(time.perf_counter() - t)
     eval_e2e = G.world * B / G.max_over_ranks(float(np.mean(te)))
+    assert np.array_equal(hout["f"], ev_out["f"].cpu().numpy())
+    del hp, hout
     tr_e = NCU_TRAFFIC_EVAL_PER_EVAL.get(name)
     rec["evals"] = {"metric": "constraint_jacobian_evaluations_per_sec", "value": G.world * B / (ms_eval * 1e-3),
                     "unit": "evaluations/s", "ms_per_step": ms_eval, "bytes_per_eval": eval_bytes,
                     "e2e": {"value": eval_e2e, "unit": "evaluations/s", "h2d_bytes_per_step": 8 * B * (L.P + L.n),
                             "d2h_bytes_per_step": 8 * B * (1 + L.n + L.m + L.m_nl * L.n),
-                            "api": "tg_eval_host (C-ABI, host buffers; copies inside the call)"},
+                            "api": "tg_eval_host (C-ABI, page-locked host buffers; copies inside the call, pipelined in chunks)"},
                     "roofline": {"kernel": "tg_eval_kernel", "bound": "hbm",
                                  "achieved": eval_bytes * B / (ms_eval * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                                  "frac": eval_bytes * B / (ms_eval * 1e-3) / 1e9 / hbm_peak,
@@ -657,12 +666,14 @@ def main():
             subs["C5"] = bench_c5_strong(G, sub_steps, 1)
         except Exception as exc:
             subs["C5"] = {"error": repr(exc)}
-        # ---- f3: problems of different shapes in ONE call (tg_solve_mixed_host) against bucket-by-bucket calls
+        # ---- f3: problems of different shapes in ONE call (tg_solve_mixed_host) against bucket-by-bucket calls; shapes
+        #      chosen from raw geometry on the device (f2 -> f3); the drop-in class on a list of containers
         if G.world == 1:
-            try:
-                subs["mixed_shapes"] = bench_mixed(G)
-            except Exception as exc:
-                subs["mixed_shapes"] = {"error": repr(exc)}
+            for key, fn in (("mixed_shapes", bench_mixed), ("shapes_from_geometry", bench_geometry), ("dropin_e2e", bench_dropin)):
+                try:
+                    subs[key] = fn(G)
+                except Exception as exc:
+                    subs[key] = {"error": repr(exc)}
         line["configs"] = subs
     if G.rank == 0:
         print(json.dumps(line), file=out_stream, flush=True)
@@ -693,6 +704,70 @@ def bench_mixed(G):
             "problems": MB * len(buckets), "unit": UNIT, "api": "tg_solve_mixed_host (C-ABI, host buffers)",
             "one_call": MB * len(buckets) / tm["one_call"], "bucket_by_bucket": MB * len(buckets) / tm["bucket_by_bucket"],
             "identical_results": bool(same)}
+
+
+def bench_geometry(G):
+    """Raw 3-D corridor polylines in (segment lengths 5 .. 11.5: 2 .. 3 intervals per corridor by the reference's rule),
+    shapes chosen on the device, boxes / parameter rows / initial guesses built on the device, one solve call."""
+    torch = G.torch
+    from trajectory_generator_b200.batched import CorridorProblems
+    rng = np.random.default_rng(20261018)
+    B, ncorr = 32768, 3
+    pts = np.zeros((B, 3, ncorr + 1))
+    pts[:, :, 0] = rng.uniform(-5, 5, (B, 3))
+    direction = rng.normal(size=(B, 3)); direction /= np.linalg.norm(direction, 2, 1)[:, None]
+    for i in range(1, ncorr + 1):
+        direction = direction + rng.normal(size=(B, 3)) * 0.35
+        direction /= np.linalg.norm(direction, 2, 1)[:, None]
+        pts[:, :, i] = pts[:, :, i - 1] + direction * rng.uniform(5, 11.5, B)[:, None]
+    pads = np.stack([rng.uniform(2, 3, (B, ncorr)), rng.uniform(2, 3, (B, ncorr)), rng.uniform(2, 4, (B, ncorr))], 2)
+    v0 = pts[:, :, 1] - pts[:, :, 0]; v0 /= np.linalg.norm(v0, 2, 1)[:, None]
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(G.dev)
+    tp, tpad, tv = t(pts), t(pads), t(v0)
+    ts = []
+    for it in range(3):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        cp = CorridorProblems(3, corridor_points=tp, corridor_pads=tpad, start_velocity=tv, end_zero_velocity=True,
+                              max_velocity=5.0, max_acceleration=0.3, objective_function_type="minimal_velocity_path")
+        out = cp.solve(jacobian=G.args.jacobian)
+        torch.cuda.synchronize()
+        if it:
+            ts.append(time.perf_counter() - t0)
+    shapes = cp.shapes()
+    return {"workload": "%d raw 3-D corridor polylines (3 corridors, segment lengths 5 .. 11.5), shapes from geometry" % B,
+            "problems": B, "shapes": len(shapes), "largest_shape": max(c for _, c in shapes), "unit": UNIT,
+            "api": "batched.CorridorProblems (tg_sfc_intervals_batch -> sort by shape key -> BatchedProblem per shape -> tg_solve_mixed_batch)",
+            "value": B / min(ts), "includes": "interval rule, grouping, corridor boxes, parameter rows, initial guesses and the solve, device tensors in / out",
+            "status0_fraction": float((out["status"] == 0).double().mean().item())}
+
+
+def bench_dropin(G):
+    """The drop-in class on a list of containers: TrajectoryGenerator.generate_trajectories(list) -- vectorised packing
+    (problem.pack_problems), H2D, solve, D2H, result objects.  Containers are built outside the clock."""
+    from trajectory_generator_b200 import synthetic
+    from trajectory_generator_b200.trajectory_generator import TrajectoryGenerator
+    from trajectory_generator_b200.problem import pack_problems
+    rec = {"unit": "containers/s", "api": "TrajectoryGenerator(d).generate_trajectories(list_of_containers)", "configs": {}}
+    for name, count in (("C2", 16384), ("C4", 8192)):
+        bt = synthetic.make(name, count)
+        items = [synthetic.container_for(bt, i) for i in range(count)]
+        d, kw = items[0][0], items[0][2]
+        ccs = [c[1] for c in items]
+        gen = TrajectoryGenerator(d)
+        ts = []
+        for it in range(3):
+            t0 = time.perf_counter()
+            res = gen.generate_trajectories(ccs, **kw)
+            if it:
+                ts.append(time.perf_counter() - t0)
+        t0 = time.perf_counter()
+        pack_problems(d, ccs, kw.get("objective_function_type", "minimal_velocity_and_time_path"), kw.get("num_intervals_free_space"))
+        tp = time.perf_counter() - t0
+        rec["configs"][name] = {"containers": count, "value": count / min(ts), "packing_only": count / tp,
+                                "status0_fraction": float(np.mean([r.status == 0 for r in res]))}
+    rec["value"] = rec["configs"]["C2"]["value"]
+    return rec
 
 
 if __name__ == "__main__":

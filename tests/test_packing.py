@@ -271,3 +271,37 @@ def test_fixed_shape_descriptors_are_the_synthetic_configurations(native_lib):
     d, cc, kw = problems.obstacles8(helpers.product_namespace())      # the C2 shape through the drop-in packer
     pp = pack_problem(d, cc)
     assert f(np.ascontiguousarray(pp.spec, dtype=np.int32).ctypes.data_as(ctypes.POINTER(ctypes.c_int))) == 1
+
+
+def test_vectorised_packing_equals_per_container_packing(native_lib):
+    """problem.pack_problems (grouped by shape, one gather per field) against pack_problem container by container:
+    every fixture problem, and the synthetic batches (where the rows must also equal the vectorised generators')."""
+    from trajectory_generator_b200 import synthetic as syn
+    from trajectory_generator_b200.problem import pack_problem, pack_problems
+    ns = helpers.product_namespace()
+    by_args = {}
+    for name, make in problems.ALL.items():
+        d, cc, kw = make(ns)
+        by_args.setdefault((d, kw.get("objective_function_type", "minimal_velocity_and_time_path"),
+                            kw.get("num_intervals_free_space")), []).append((name, cc))
+    for (d, obj, nifs), items in by_args.items():
+        groups = pack_problems(d, [cc for _, cc in items], obj, nifs)
+        assert sorted(int(i) for g in groups for i in g.indices) == list(range(len(items)))
+        for g in groups:
+            for row, i in enumerate(g.indices):
+                name, cc = items[int(i)]
+                pp = pack_problem(d, cc, obj, nifs)
+                assert np.array_equal(g.spec, pp.spec), name
+                assert np.array_equal(g.par[row], pp.par), name
+                assert np.array_equal(g.x0[row], np.clip(pp.x0, pp.xl, pp.xu)), name
+                assert np.array_equal(g.xl, pp.xl) and np.array_equal(g.xu, pp.xu), name
+    for cfg in ("C2", "C3", "C4", "C5a"):
+        b = syn.make(cfg, 48)
+        items = [syn.container_for(b, i) for i in range(48)]
+        d, kw = items[0][0], items[0][2]
+        groups = pack_problems(d, [cc for _, cc, _ in items], kw.get("objective_function_type", syn.OBJECTIVE[cfg]),
+                               kw.get("num_intervals_free_space"))
+        assert len(groups) == 1 and np.array_equal(groups[0].indices, np.arange(48))
+        assert np.array_equal(groups[0].spec, b.spec)
+        assert np.abs(groups[0].par - b.par).max() <= 1e-12 * max(1.0, np.abs(b.par).max())
+        assert np.abs(groups[0].x0 - b.x0).max() <= 1e-12 * max(1.0, np.abs(b.x0).max())

@@ -124,14 +124,28 @@ def _np_ptr(a):
     return ctypes.c_void_p(0 if a is None else a.ctypes.data)
 
 
-def evaluate_host(spec, par, x, want=("f", "g", "c", "jnl")):
-    """Host-buffer M1 evaluation through tg_eval_host (numpy in, numpy out; copies inside the call)."""
+def pinned_empty(shape, dtype=np.float64):
+    """numpy array backed by page-locked host memory (torch owns it): the host-buffer entry points copy such buffers with
+    the DMA engines asynchronously and pipeline a batch in chunks; pageable arrays work too, one synchronous chunk."""
+    torch = _torch()
+    t = torch.empty(tuple(shape), dtype={np.float64: torch.float64, np.int32: torch.int32}[dtype]).pin_memory()
+    return t.numpy()
+
+
+def evaluate_host(spec, par, x, want=("f", "g", "c", "jnl"), out=None):
+    """Host-buffer M1 evaluation through tg_eval_host (numpy in, numpy out; copies inside the call).  `out`: dict of
+    arrays to write into (e.g. ``pinned_empty`` buffers kept between calls); missing entries are allocated."""
     lay = Layout(spec)
     par = np.ascontiguousarray(par, dtype=np.float64).reshape(-1, lay.P)
     x = np.ascontiguousarray(x, dtype=np.float64).reshape(-1, lay.n)
     B = x.shape[0]
     shapes = {"f": (B,), "g": (B, lay.n), "c": (B, lay.m), "jnl": (B, lay.m_nl, lay.n)}
-    res = {k: np.empty(shapes[k]) for k in want}
+    res = out if out is not None else {}
+    for k in want:
+        if k not in res:
+            res[k] = np.empty(shapes[k])
+        elif res[k].shape != shapes[k] or res[k].dtype != np.float64 or not res[k].flags.c_contiguous:
+            raise ValueError("out[%r] must be a contiguous float64 array of shape %r" % (k, shapes[k]))
     spec, sp = _native.spec_ptr(spec)
     rc = _native.lib().tg_eval_host(sp, B, _np_ptr(par), _np_ptr(x), _np_ptr(res.get("f")), _np_ptr(res.get("g")),
                                     _np_ptr(res.get("c")), _np_ptr(res.get("jnl")))

@@ -11,6 +11,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <initializer_list>
 #include <mutex>
 #include <atomic>
 #include <string>
@@ -536,6 +537,7 @@ struct DevBuf {
 struct TgHostCtx {
     std::mutex mu;
     DevBuf par, x, f, g, c, j, i, ws;
+    cudaStream_t st[2] = {nullptr, nullptr};      // chunk pipeline of tg_eval_host
 };
 static TgHostCtx g_host[TG_MAX_DEVICES];
 static TgHostCtx *tg_host_ctx()
@@ -544,6 +546,21 @@ static TgHostCtx *tg_host_ctx()
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= TG_MAX_DEVICES) return nullptr;
     return &g_host[dev];
 }
+
+// true when every non-NULL pointer is page-locked host memory (cudaHostAlloc / cudaHostRegister / torch pin_memory):
+// such buffers are copied by the DMA engines asynchronously, so chunks of a batch can overlap their copies and kernels
+static bool tg_all_pinned(std::initializer_list<const void *> ptrs)
+{
+    for (const void *p : ptrs) {
+        if (!p) continue;
+        cudaPointerAttributes a;
+        if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+        if (a.type != cudaMemoryTypeHost) return false;
+    }
+    return true;
+}
+
+#define TG_HOST_CHUNKS 8          // pipeline depth of the host-buffer entry points on page-locked buffers
 
 extern "C" int tg_eval_host(const int *spec, int B, const double *par, const double *x, double *f, double *g, double *c,
                             double *jnl)
@@ -564,16 +581,35 @@ extern "C" int tg_eval_host(const int *spec, int B, const double *par, const dou
     if (g && (rc = g_g.ensure((size_t)B * L.n * nb))) return rc;
     if (c && (rc = g_c.ensure((size_t)B * (L.m + 1) * nb))) return rc;
     if (jnl && (rc = g_j.ensure((size_t)B * (L.m_nl * L.n + 1) * nb))) return rc;
-    TG_CUDA(cudaMemcpyAsync(g_par.p, par, (size_t)B * L.P * nb, cudaMemcpyHostToDevice, 0));
-    TG_CUDA(cudaMemcpyAsync(g_x.p, x, (size_t)B * L.n * nb, cudaMemcpyHostToDevice, 0));
-    rc = tg_eval_batch(spec, B, (const double *)g_par.p, (const double *)g_x.p, f ? (double *)g_f.p : nullptr,
-                       g ? (double *)g_g.p : nullptr, c ? (double *)g_c.p : nullptr, jnl ? (double *)g_j.p : nullptr, 0);
-    if (rc) return rc;
-    if (f) TG_CUDA(cudaMemcpyAsync(f, g_f.p, (size_t)B * nb, cudaMemcpyDeviceToHost, 0));
-    if (g) TG_CUDA(cudaMemcpyAsync(g, g_g.p, (size_t)B * L.n * nb, cudaMemcpyDeviceToHost, 0));
-    if (c) TG_CUDA(cudaMemcpyAsync(c, g_c.p, (size_t)B * L.m * nb, cudaMemcpyDeviceToHost, 0));
-    if (jnl) TG_CUDA(cudaMemcpyAsync(jnl, g_j.p, (size_t)B * L.m_nl * L.n * nb, cudaMemcpyDeviceToHost, 0));
-    TG_CUDA(cudaStreamSynchronize(0));
+    // Page-locked caller buffers: the batch goes through in chunks on two streams, so the upload of one chunk, the
+    // kernel of another and the download of a third (the dense Jacobian rows: ~85 % of the bytes) overlap.  Pageable
+    // buffers are staged by the driver synchronously: one chunk.
+    const bool pinned = B >= 4096 && tg_all_pinned({par, x, f, g, c, jnl});
+    const int chunks = pinned ? TG_HOST_CHUNKS : 1;
+    cudaStream_t st[2] = {0, 0};
+    if (pinned) {
+        for (int k = 0; k < 2; k++) {
+            if (!H->st[k]) TG_CUDA(cudaStreamCreateWithFlags(&H->st[k], cudaStreamNonBlocking));
+            st[k] = H->st[k];
+        }
+    }
+    for (int k = 0; k < chunks; k++) {
+        const size_t lo = (size_t)B * k / chunks, hi = (size_t)B * (k + 1) / chunks, cnt = hi - lo;
+        if (!cnt) continue;
+        cudaStream_t s = st[k & 1];
+        double *dpar = (double *)g_par.p + lo * L.P, *dx = (double *)g_x.p + lo * L.n;
+        double *df = f ? (double *)g_f.p + lo : nullptr, *dg = g ? (double *)g_g.p + lo * L.n : nullptr;
+        double *dc = c ? (double *)g_c.p + lo * L.m : nullptr, *dj = jnl ? (double *)g_j.p + lo * L.m_nl * L.n : nullptr;
+        TG_CUDA(cudaMemcpyAsync(dpar, par + lo * L.P, cnt * L.P * nb, cudaMemcpyHostToDevice, s));
+        TG_CUDA(cudaMemcpyAsync(dx, x + lo * L.n, cnt * L.n * nb, cudaMemcpyHostToDevice, s));
+        if ((rc = tg_eval_batch(spec, (int)cnt, dpar, dx, df, dg, dc, dj, s))) return rc;
+        if (f) TG_CUDA(cudaMemcpyAsync(f + lo, df, cnt * nb, cudaMemcpyDeviceToHost, s));
+        if (g) TG_CUDA(cudaMemcpyAsync(g + lo * L.n, dg, cnt * L.n * nb, cudaMemcpyDeviceToHost, s));
+        if (c) TG_CUDA(cudaMemcpyAsync(c + lo * L.m, dc, cnt * L.m * nb, cudaMemcpyDeviceToHost, s));
+        if (jnl) TG_CUDA(cudaMemcpyAsync(jnl + lo * L.m_nl * L.n, dj, cnt * L.m_nl * L.n * nb, cudaMemcpyDeviceToHost, s));
+    }
+    TG_CUDA(cudaStreamSynchronize(st[0]));
+    if (pinned) TG_CUDA(cudaStreamSynchronize(st[1]));
     return 0;
 }
 

@@ -301,3 +301,246 @@ def _pack_path_problem(d, cc, objective_function_type, num_intervals_free_space_
     if obstacles is not None:
         par += _obstacle_blocks(spec, obstacles, d)
     return _finish_packing(d, N, spec, par, wd, sfc, initial_control_points_arg, initial_scale_factor)
+
+
+# --------------------------------------------------------------------------------------------------------------
+# Vectorised packing of MANY containers (the batched addition generate_trajectories): containers are grouped by a
+# shape key read off their fields without any array arithmetic, and each group is packed with one numpy gather per
+# field -- the same descriptor, parameter-row order, initial variables and bounds as pack_problem (checked against
+# it container by container in tests/test_packing.py).
+# --------------------------------------------------------------------------------------------------------------
+def _is_zero(v):
+    """velocity given and identically zero (Waypoint.checkIfZeroVel without the norm: early exit on the first entry)"""
+    if v is None:
+        return False
+    for e in np.asarray(v).flat:
+        if e != 0:
+            return False
+    return True
+
+
+def _shape_key(cc, d):
+    """Everything that decides the descriptor, as a hashable tuple (no numpy arithmetic)."""
+    wd, db, tb = cc.waypoint_constraints, cc.derivative_constraints, cc.turning_constraint
+    sfc, obstacles = cc.sfc_constraints, cc.obstacle_constraints
+    key = []
+    for wp in (wd.start_waypoint, wd.end_waypoint):
+        zero = _is_zero(wp.velocity)
+        key.append((wp.direction is not None, wp.velocity is not None, zero, wp.acceleration is not None, bool(wp.is_target)))
+    key.append((wd.get_num_intermediate_waypoints(), wd.intermediate_velocities is not None))
+    if db is None:
+        key.append(None)
+    else:
+        key.append((db.min_velocity is not None, db.max_velocity is not None, db.max_upward_velocity is not None,
+                    db.max_horizontal_velocity is not None, db.max_acceleration is not None, db.gravity is not None,
+                    db.max_jerk is not None, db.min_tangential_acceleration is not None and db.max_tangential_acceleration is not None))
+    key.append(None if tb is None or tb.max_turning_bound is None else tb.bound_type)
+    if sfc is None:
+        key.append(None)
+    else:
+        ipc = getattr(sfc, "_tg_ipc_key", None)          # cached on the object (SFC_Data fixes its intervals at construction)
+        if ipc is None:
+            raw = sfc.get_intervals_per_corridor()
+            ipc = (int(raw),) if np.ndim(raw) == 0 else tuple(int(v) for v in raw)
+            try:
+                sfc._tg_ipc_key = ipc
+            except Exception:
+                pass
+        key.append(ipc)
+    key.append(None if obstacles is None else len(obstacles))
+    return tuple(key)
+
+
+def line_initial_points(start, goal, N):
+    """np.linspace(start, goal, N) per problem (TG/objectives/objective_variables.py:63-70) -> [B, d, N]"""
+    # numpy.linspace: arange * step + start, except that a zero step in ANY coordinate switches the whole call to
+    # (arange / div) * delta + start (numpy/_core/function_base.py: any_step_zero)
+    delta = goal - start
+    div = N - 1
+    step = delta / div
+    ar = np.arange(N, dtype=np.float64)[None, None, :]
+    cps = ar * step[:, :, None] + start[:, :, None]
+    zero = (step == 0).any(1)
+    if zero.any():
+        cps[zero] = (ar / div) * delta[zero][:, :, None] + start[zero][:, :, None]
+    cps[:, :, -1] = goal
+    return cps
+
+
+def polyline_initial_points(seq, N):
+    """Equal arc-length steps along a polyline (TG/objectives/objective_variables.py:63-93), batched.
+    seq: [B, d, S+1] -> [B, d, N]."""
+    B, d, S1 = seq.shape
+    S = S1 - 1
+    seglen = np.linalg.norm(seq[:, :, 1:] - seq[:, :, :-1], 2, 1)
+    cum = np.cumsum(seglen, 1)
+    spacing = cum[:, S - 1] / (N - 1)
+    rows = np.arange(B)
+    seg = np.zeros(B, dtype=np.int64)
+    walked = np.zeros(B)
+    anchor = seq[:, :, 0].copy()
+    step = np.zeros(B)
+    cps = np.empty((B, d, N))
+    for i in range(N - 1):
+        sg = np.minimum(seg, S - 1)
+        heading = seq[rows, :, sg + 1] - seq[rows, :, sg]
+        heading = heading / np.linalg.norm(heading, 2, 1)[:, None]
+        cps[:, :, i] = anchor + heading * step[:, None]
+        anchor = cps[:, :, i].copy()
+        step = spacing.copy()
+        walked = walked + step
+        adv = cum[rows, sg] < walked
+        step = np.where(adv, walked - cum[rows, sg], step)
+        seg = seg + adv
+        nxt = seq[rows, :, np.minimum(seg, S)]
+        anchor = np.where(adv[:, None], nxt, anchor)
+    cps[:, :, -1] = seq[:, :, -1]
+    return cps
+
+
+class PackedGroup:
+    """B containers of one shape: spec, par [B, P], x0 [B, n] (clipped to the bounds), xl / xu [n], and the positions
+    of the containers in the input list."""
+
+    def __init__(self, indices, spec, par, x0, xl, xu):
+        self.indices, self.spec, self.par, self.x0, self.xl, self.xu = indices, spec, par, x0, xl, xu
+        self.layout = Layout(spec)
+
+
+def pack_problems(dimension, containers, objective_function_type="minimal_velocity_and_time_path",
+                  num_intervals_free_space_arg=None):
+    """-> list of PackedGroup, one per shape, covering every container (default initial guesses)."""
+    d = int(dimension)
+    if objective_function_type not in OBJECTIVES:
+        raise Exception("Error, Invalid objective function type")
+    groups = {}
+    for i, cc in enumerate(containers):
+        groups.setdefault(_shape_key(cc, d), []).append(i)
+    out = []
+    def col(items):
+        """list of B column vectors (d x 1, the form the dataclasses hold) -> [B, d]"""
+        items = list(items)
+        try:
+            a = np.concatenate(items, axis=1)               # fast path: every item is a 2-D float column
+            if a.ndim == 2 and a.dtype == np.float64 and a.shape[1] == len(items):
+                return np.ascontiguousarray(a.T)
+        except Exception:
+            pass
+        return np.array([np.asarray(v, dtype=np.float64).reshape(-1) for v in items])
+    for key, idx in groups.items():
+        (s_dir, s_vel, s_zero, s_acc, _), (e_dir, e_vel, e_zero, e_acc, e_target), (niw, iw_vel), dbk, turn, ipc, nobst = key
+        group = [containers[i] for i in idx]
+        B = len(group)
+        wds = [c.waypoint_constraints for c in group]
+        sws = [w.start_waypoint for w in wds]
+        ews = [w.end_waypoint for w in wds]
+        # ---- sizes (TG/trajectory_generator.py:134-162)
+        if ipc is not None:
+            nint = sum(ipc)
+        elif num_intervals_free_space_arg is not None:
+            nint = num_intervals_free_space_arg
+        else:
+            nint = 5 + 2 * int(s_zero) + 2 * int(e_zero) + int(s_zero and e_zero)
+        N = int(nint + 3)
+        spec = np.zeros(SP_COUNT, dtype=np.int32)
+        spec[SP_DIM], spec[SP_NCP] = d, N
+        spec[SP_OBJECTIVE] = OBJECTIVES.index(objective_function_type)
+        spec[SP_START_KIND] = 1 if s_zero else 0
+        spec[SP_END_KIND] = 1 if e_zero else (2 if e_target else 0)
+        start = col(w.location for w in sws)
+        goal = col(w.location for w in ews)
+        par = [start, goal]
+        if spec[SP_END_KIND] == 2:
+            par.append(col(w.velocity for w in ews))
+        # ---- terminal derivative rows (CF/waypoint_constraints.py:73-120), as pack_problem
+        for wps, (has_dir, has_vel, zero, has_acc), (f_dir, f_vel, f_acc) in (
+                (sws, (s_dir, s_vel, s_zero, s_acc), (SP_START_DIR, SP_START_VEL, SP_START_ACC)),
+                (ews, (e_dir, e_vel, e_zero, e_acc), (SP_END_DIR, SP_END_VEL, SP_END_ACC))):
+            if not (has_acc or has_dir or not zero):          # Waypoint.checkIfDerivativesActive
+                continue
+            if has_dir:
+                spec[f_dir] = 2 if (has_vel and zero) else 1
+                par.append(col(w.direction for w in wps))
+            if has_vel and not zero:
+                spec[f_vel] = 1
+                par.append(col(w.velocity for w in wps))
+            if has_acc:
+                spec[f_acc] = 1
+                par.append(col(w.acceleration for w in wps))
+            if not (spec[f_dir] or spec[f_vel] or spec[f_acc]):
+                raise IndexError("terminal waypoint needs a velocity, direction or acceleration")
+        spec[SP_NIW] = niw
+        if niw:
+            par.append(col(w.intermediate_locations for w in wds))
+            if iw_vel:
+                spec[SP_IW_VEL] = 1
+                par.append(col(w.intermediate_velocities for w in wds))
+        # ---- derivative bounds
+        if dbk is not None:
+            dbs = [c.derivative_constraints for c in group]
+            minv, maxv, up, horiz, maxa, grav, jerk, tang = dbk
+            if minv or maxv or maxa or jerk:                  # DerivativeBounds.checkIfDerivativesActive
+                for flag, present, name in ((SP_DB_MINV, minv, "min_velocity"), (SP_DB_MAXV, maxv, "max_velocity"),
+                                            (SP_DB_UP, up, "max_upward_velocity"), (SP_DB_HORIZ, horiz, "max_horizontal_velocity"),
+                                            (SP_DB_MAXA, maxa, "max_acceleration"), (SP_DB_GRAV, grav and maxa, "gravity"),
+                                            (SP_DB_JERK, jerk, "max_jerk")):
+                    if present:
+                        spec[flag] = 1
+                        par.append(np.array([[float(getattr(b, name))] for b in dbs]))
+            if tang:
+                spec[SP_TANG] = 1
+                par.append(np.array([[float(b.min_tangential_acceleration), float(b.max_tangential_acceleration)] for b in dbs]))
+        if turn is not None:
+            spec[SP_TURN] = TURN_KINDS[turn]
+            par.append(np.array([[float(c.turning_constraint.max_turning_bound)] for c in group]))
+        # ---- corridors (CF/sfc_constraints.py:7-77), obstacles (CF/obstacle_constraints.py:93-113)
+        seq = None
+        if ipc is not None:
+            if len(ipc) > MAX_CORRIDORS:
+                raise Exception("at most %d corridors are supported" % MAX_CORRIDORS)
+            spec[SP_NCORR] = len(ipc)
+            spec[SP_IPC0:SP_IPC0 + len(ipc)] = ipc
+            boxes = [c.sfc_constraints.get_sfc_list()[:len(ipc)] for c in group]
+            flat = [bx for bl in boxes for bx in bl]
+            nc = len(ipc)
+            rot = np.transpose(np.array([bx.rotation for bx in flat], dtype=np.float64), (0, 2, 1)).reshape(B, nc, d * d)      # R^T row-major
+            tr = col(bx.translation for bx in flat).reshape(B, nc, d)
+            half = col(bx.dimensions for bx in flat).reshape(B, nc, d) / 2
+            par.append(np.concatenate([rot, tr - half, tr + half], 2).reshape(B, -1))
+            seq = np.array([np.asarray(c.sfc_constraints.get_point_sequence(), dtype=np.float64) for c in group])
+        if nobst is not None:
+            spec[SP_NOBST] = nobst
+            obs = [o for c in group for o in c.obstacle_constraints]
+            ctr = col(o.center for o in obs).reshape(B, nobst, d)
+            par.append(np.transpose(ctr, (0, 2, 1)).reshape(B, -1))
+            par.append(np.array([o.radius for o in obs], dtype=np.float64).reshape(B, nobst))
+        par = np.ascontiguousarray(np.concatenate(par, 1), dtype=np.float64)
+        lay = Layout(spec)
+        if lay.P != par.shape[1]:
+            raise RuntimeError("parameter rows have %d entries, layout expects %d" % (par.shape[1], lay.P))
+        # ---- initial variables and bounds (TG/objectives/objective_variables.py:27-105)
+        wseq = None
+        if niw:
+            wseq = np.concatenate([start[:, :, None], np.array([w.intermediate_locations for w in wds], dtype=np.float64),
+                                   goal[:, :, None]], 2)
+        if seq is None:
+            seq = wseq if wseq is not None else np.stack([start, goal], 2)
+        cps = line_initial_points(seq[:, :, 0], seq[:, :, 1], N) if seq.shape[2] == 2 else polyline_initial_points(seq, N)
+        n = lay.n
+        x0 = np.empty((B, n))
+        x0[:, :d * N] = cps.reshape(B, -1)
+        x0[:, d * N:d * N + 1 + lay.nws] = 1.0
+        if niw:
+            if wseq.shape[2] - 1 <= 2:
+                x0[:, lay.it0:] = 0.5
+            else:
+                cum = np.cumsum(np.linalg.norm(wseq[:, :, 1:] - wseq[:, :, :-1], 2, 1), 1)
+                x0[:, lay.it0:] = (cum / cum[:, -1:])[:, :-1] * (N - 3)
+        xl = np.full(n, -np.inf)
+        xu = np.full(n, np.inf)
+        xl[d * N:d * N + 1 + lay.nws] = VARIABLE_LOWER_BOUND
+        if niw:
+            xl[lay.it0:] = 0.0
+            xu[lay.it0:] = N - 3
+        out.append(PackedGroup(np.asarray(idx), spec, par, np.clip(x0, xl, xu), xl, xu))
+    return out

@@ -60,44 +60,10 @@ def _spec(d, N, objective, **flags):
 
 def _line_init(s, g, N):
     """np.linspace(start, end, N) per problem -> [B, d*N] (row-major d x N)."""
-    t = np.linspace(0.0, 1.0, N)
-    # np.linspace computes start + step*i with step = (stop-start)/(N-1); keep that arithmetic
-    step = (g - s) / (N - 1)
-    cps = s[:, :, None] + step[:, :, None] * np.arange(N)[None, None, :]
-    cps[:, :, -1] = g
-    del t
-    return cps.reshape(len(s), -1)
+    return pk.line_initial_points(s, g, N).reshape(len(s), -1)
 
 
-def _polyline_init(seq, N):
-    """Equal arc-length steps along a polyline (TG/objectives/objective_variables.py:63-93), batched.
-    seq: [B, d, S+1] -> [B, d, N]."""
-    B, d, S1 = seq.shape
-    S = S1 - 1
-    seglen = np.linalg.norm(seq[:, :, 1:] - seq[:, :, :-1], 2, 1)
-    cum = np.cumsum(seglen, 1)
-    spacing = cum[:, S - 1] / (N - 1)
-    rows = np.arange(B)
-    seg = np.zeros(B, dtype=np.int64)
-    walked = np.zeros(B)
-    anchor = seq[:, :, 0].copy()
-    step = np.zeros(B)
-    cps = np.empty((B, d, N))
-    for i in range(N - 1):
-        sg = np.minimum(seg, S - 1)
-        heading = seq[rows, :, sg + 1] - seq[rows, :, sg]
-        heading = heading / np.linalg.norm(heading, 2, 1)[:, None]
-        cps[:, :, i] = anchor + heading * step[:, None]
-        anchor = cps[:, :, i].copy()
-        step = spacing.copy()
-        walked = walked + step
-        adv = cum[rows, sg] < walked
-        step = np.where(adv, walked - cum[rows, sg], step)
-        seg = seg + adv
-        nxt = seq[rows, :, np.minimum(seg, S)]
-        anchor = np.where(adv[:, None], nxt, anchor)
-    cps[:, :, -1] = seq[:, :, -1]
-    return cps
+_polyline_init = pk.polyline_initial_points
 
 
 def _heading(theta):

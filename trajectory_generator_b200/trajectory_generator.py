@@ -11,7 +11,7 @@ import numpy as np
 from . import batch
 from .constraint_data_structures.constraints_container import ConstraintsContainer
 from .constraint_data_structures.waypoint_data import Waypoint
-from .problem import pack_problem
+from .problem import pack_problem, pack_problems
 
 
 class TrajectoryResult:
@@ -67,26 +67,34 @@ class TrajectoryGenerator:
         """Solves every container; problems of identical shape share one kernel launch.
         Returns a list of TrajectoryResult in input order."""
         count = len(containers)
-        icps = initial_control_points if initial_control_points is not None else [None] * count
-        isfs = initial_scale_factors if initial_scale_factors is not None else [None] * count
-        packed = [pack_problem(self._dimension, cc, objective_function_type, num_intervals_free_space, icps[i], isfs[i])
-                  for i, cc in enumerate(containers)]
-        groups = {}
-        for i, p in enumerate(packed):
-            groups.setdefault(p.key, []).append(i)
         results = [None] * count
-        order = list(groups.values())
-        buckets = [(packed[idx[0]].spec, np.stack([packed[i].par for i in idx]),
-                    np.stack([np.clip(packed[i].x0, packed[i].xl, packed[i].xu) for i in idx])) for idx in order]
+        if initial_control_points is None and initial_scale_factors is None:
+            # vectorised packing: containers grouped by shape, one numpy gather per field (problem.pack_problems)
+            groups = pack_problems(self._dimension, containers, objective_function_type, num_intervals_free_space)
+            order = [g.indices for g in groups]
+            layouts = [g.layout for g in groups]
+            buckets = [(g.spec, g.par, g.x0) for g in groups]
+        else:
+            icps = initial_control_points if initial_control_points is not None else [None] * count
+            isfs = initial_scale_factors if initial_scale_factors is not None else [None] * count
+            packed = [pack_problem(self._dimension, cc, objective_function_type, num_intervals_free_space, icps[i], isfs[i])
+                      for i, cc in enumerate(containers)]
+            by_key = {}
+            for i, p in enumerate(packed):
+                by_key.setdefault(p.key, []).append(i)
+            order = list(by_key.values())
+            layouts = [packed[idx[0]].layout for idx in order]
+            buckets = [(packed[idx[0]].spec, np.stack([packed[i].par for i in idx]),
+                        np.stack([np.clip(packed[i].x0, packed[i].xl, packed[i].xu) for i in idx])) for idx in order]
         if len(buckets) == 1:
             outs = [batch.solve_host(*buckets[0], self._maxiter, self._ftol, self._jacobian)]
         else:       # different shapes: one call, the buckets' solves overlap on the device (tg_solve_mixed_host)
             outs = batch.solve_mixed_host(buckets, self._maxiter, self._ftol, self._jacobian)
-        for idx, out in zip(order, outs):
-            lay = packed[idx[0]].layout
+        for idx, lay, out in zip(order, layouts, outs):
+            xs = out["x"]
+            cps_all = xs[:, :lay.d * lay.N].reshape(len(idx), lay.d, lay.N).copy()
+            scales = xs[:, lay.ia].tolist(); viol = out["violation"].tolist(); status = out["status"].tolist()
+            nit = out["nit"].tolist(); fs = out["f"].tolist()
             for k, i in enumerate(idx):
-                x = out["x"][k]
-                cps = np.reshape(x[:lay.d * lay.N], (lay.d, lay.N)).copy()
-                results[i] = TrajectoryResult(cps, float(x[lay.ia]), bool(out["violation"][k]), int(out["status"][k]),
-                                              int(out["nit"][k]), float(out["f"][k]), x.copy())
+                results[i] = TrajectoryResult(cps_all[k], scales[k], bool(viol[k]), status[k], nit[k], fs[k], xs[k])
         return results
