@@ -3,4 +3,6 @@
 #define TG_SFX _g8
 #define TG_INLINE_ALL
 #define TG_INLINE_LEAVES 1
+// fixed shapes (tg_shape.h) with instantiations in this translation unit
+#define TG_EVAL_FIXED TG_FIXED_CASE(TG_FIX_C2) TG_FIXED_CASE(TG_FIX_C4) TG_FIXED_CASE(TG_FIX_C5A) TG_FIXED_CASE(TG_FIX_C5C)
 #include "tg_kernels_eval.inc"

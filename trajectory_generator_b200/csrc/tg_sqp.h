@@ -897,7 +897,10 @@ TG_FN void tg_sqp_stage_der(const TgLayout &L, const int *sp, const double *par,
 // staged in shared memory).  The factor L is then copied once into the storage of J (free until the QP is set up),
 // updated there, written back once and handed to the QP set-up from there, instead of being read five times and
 // written twice through L2.  Same arithmetic.
-template <bool LM_FAR>
+// SPLIT_NQ (instantiations with a compile-time descriptor): the plain subproblem (n variables) and the augmented one
+// (n + 1) get a copy of the solver each, so that the plain one -- all but a few per cent of the calls -- runs with a
+// constant number of variables: loop bounds of the products known, no remainder handling.
+template <bool LM_FAR, bool SPLIT_NQ = false>
 TG_QFN void tg_sqp_stage_qp(const TgLayout &L, const TgSqpWs &W)
 {
     // the update's scratch (5 n doubles) comes from R's storage when L sits in J's
@@ -1031,8 +1034,11 @@ TG_QFN void tg_sqp_stage_qp(const TgLayout &L, const TgSqpWs &W)
                     for (int i = 0; i < n; i++) dmax = fmax(dmax, W.Dd[i]);
                     dfloor = 1e-10 * dmax;
                 }
-                // (one call site: the solver is inlined.  Only its first loop, which packs L next to J, reads Lsrc)
-                mode = tg_qp_solve(W, (lm_far && lcopy) ? W.Jq : W.Lm, nq, meq, rho, fl, ctl.nract, dfloor);
+                // (one call site per number of variables: the solver is inlined.  Only its first loop, which packs L next
+                // to J, reads Lsrc)
+                const double *Lsrc = (lm_far && lcopy) ? W.Jq : W.Lm;
+                if (SPLIT_NQ && nq == n) mode = tg_qp_solve(W, Lsrc, n, meq, rho, fl, ctl.nract, dfloor);
+                else mode = tg_qp_solve(W, Lsrc, nq, meq, rho, fl, ctl.nract, dfloor);
                 lcopy = false;        // the copy shared J's storage: the solve has overwritten it
                 if (attempt == 0 && mode == 6 && n == meq) mode = 4;
                 if (mode == TG_QP_OK) break;
