@@ -103,7 +103,7 @@ static inline cudaError_t tg_allow_shared_memory(K kernel)
                                     double *c, double *jnl, int sm_count, int smem_optin, cudaStream_t st);               \
     cudaError_t tg_launch_linear##SFX(const TgShape &S, int B, const double *par, double *alin, int sm_count,             \
                                       cudaStream_t st);                                                                   \
-    size_t tg_eval_smem##SFX(const TgShape &S);                                                                           \
+    size_t tg_eval_smem##SFX(const TgShape &S, bool sink_c);                                                                           \
     cudaError_t tg_launch_begin##SFX(const TgShape &S, int B, const double *x, double *pws, size_t np, int maxiter,       \
                                      double ftol, int flags, TgRoundCtl *rc, int *list0, cudaStream_t st);                \
     cudaError_t tg_launch_ls##SFX(const TgShape &S, int B, const double *par, double *pws, size_t np, size_t smem,        \
