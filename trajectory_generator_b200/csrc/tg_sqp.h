@@ -79,7 +79,7 @@ TG_HD int tg_rp(int j) { return j * (j + 1) / 2; }      // offset of column j of
 #define TG_QFN TG_FN
 #endif
 
-// Carves the per-problem state.  The persistent block is [ctl | x xl xu g s x0 | c mu | gl r Lm Dd | ract rot | A]; its first
+// Carves the per-problem state.  The persistent block is [ctl | x xl xu g s x0 | c mu | gl r Dd | ract rot | A | Lm]; its first
 // `npre` doubles (everything the line-search stage touches except A) may be staged at `prefix` while the rest
 // stays at `pbase` (+ offset) -- pass prefix == pbase for one contiguous block.  The scratch block is
 // [QP-stage scratch | evaluation scratch (cf, evaluators' scratch)]; `ebase` != 0 places the evaluation scratch
@@ -102,10 +102,11 @@ TG_HD void tg_sqp_carve4(const TgLayout &L, double *prefix, double *pbase, doubl
     if (npre_) *npre_ = o;
     base = pbase;
     TG_TAKE(gl, n1); TG_TAKE(r, w.nc + 1);
-    TG_TAKE(Lm, n * n); TG_TAKE(Dd, n1);
+    TG_TAKE(Dd, n1);
     w.ract = (int *)(base + o); o += (size_t)(n1 / 2 + 1);
     TG_TAKE(rot, L.n_sfc ? L.nint * L.d * L.d : 0);
     TG_TAKE(A, w.lda * n1);
+    TG_TAKE(Lm, n * n);          // last: the lock-step QP kernel stages everything in front of it and leaves L in global memory
     if (np_) *np_ = o;
     o = 0; base = sbase;
     TG_TAKE(u, n1); TG_TAKE(v, n1); TG_TAKE(w, n1);
