@@ -180,14 +180,22 @@ def features2d(ns):
     return 2, cc, dict(objective_function_type="minimal_time_path_velocity_penalty")
 
 
+def distance_time2d(ns):
+    """Coverage problem: the one objective no demo uses, `minimal_distance_and_time_path` (TG/objectives/
+    objective_functions.py:27-33), on the obstacle2d constraints."""
+    d, cc, kw = obstacle2d(ns)
+    return d, cc, dict(objective_function_type="minimal_distance_and_time_path")
+
+
 ALL = dict(c1_sfc2d=c1_sfc2d, c1_curvature=c1_curvature, obstacle2d=obstacle2d, obstacles8=obstacles8,
            intermediate_waypoints=intermediate_waypoints, intermediate_curvature=intermediate_curvature,
            sfc3d=sfc3d, sfc3d_four=sfc3d_four, sfc_obstacles3d=sfc_obstacles3d, bicycle3=bicycle3, unicycle2=unicycle2,
-           bicycle_tangential=bicycle_tangential, features3d=features3d, features2d=features2d)
+           bicycle_tangential=bicycle_tangential, features3d=features3d, features2d=features2d,
+           distance_time2d=distance_time2d)
 
 # problems whose reference solve finishes in a few seconds (solve results are recorded for these)
 SOLVE = ("c1_sfc2d", "c1_curvature", "obstacle2d", "obstacles8", "sfc3d", "sfc3d_four", "sfc_obstacles3d", "bicycle3",
-         "unicycle2", "intermediate_waypoints")
+         "unicycle2", "intermediate_waypoints", "distance_time2d")
 
 
 def test_point(x0, d, N, seed):

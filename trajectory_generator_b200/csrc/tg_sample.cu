@@ -68,7 +68,7 @@ __device__ __forceinline__ double ipow(double x, int e)
 // one sample: trajectory b (control points P, scale sf, derivative weights kd), sample index k
 template <int MODE, int RTH, int D, int ORD>
 __device__ __forceinline__ void tg_sample_one(const SampleArgs &a, int b, int k, const double *P, double sf, const double kd[ORD + 1],
-                                              int num, double step, double off, double last)
+                                              int num, double step, double off, double last, double v[D])
 {
     const int nint = a.N - ORD, div = num - 1;
     constexpr int d = D;
@@ -81,16 +81,15 @@ __device__ __forceinline__ void tg_sample_one(const SampleArgs &a, int b, int k,
         if (a.times) a.times[(long)b * per + k] = tdata;
         t = __ddiv_rn(tdata, sf);
     }
-    double *o = a.out + ((long)b * d) * per + k;
     if (!(t >= 0.0) || t > (double)nint) {          // dropped by the reference's masks: the array keeps its zero
 #pragma unroll
-        for (int c = 0; c < d; c++) o[(long)c * per] = 0.0;
+        for (int c = 0; c < d; c++) v[c] = 0.0;
         return;
     }
     int i = (int)t;
     if (i > nint - 1) i = nint - 1;
     const double tau = t - (double)i;
-    // weights of the four control points: M (K L_r)  (TG/matrix_evaluation.py:26-29, 127-130 with the products
+    // weights of the order + 1 control points: M (K L_r)  (TG/matrix_evaluation.py:26-29, 127-130 with the products
     // associated as P (M L); the reference forms (P M) L -- the same sums up to the last place)
     double wl[ORD + 1], w[ORD + 1];
 #pragma unroll
@@ -109,12 +108,14 @@ __device__ __forceinline__ void tg_sample_one(const SampleArgs &a, int b, int k,
         double h = p[0] * wl[0];
 #pragma unroll
         for (int l = 1; l <= ORD; l++) h = h + p[l] * wl[l];
-        o[(long)c * per] = h;
+        v[c] = h;
     }
 }
 
 // Work item = (trajectory, chunk of 256 consecutive samples), handed to warps in a grid-stride loop: no block-level
-// synchronisation, the per-trajectory set-up is shared by 8 samples per lane, coalesced 8-byte stores per coordinate row.
+// synchronisation, the per-trajectory set-up is shared by 8 samples per lane.  A lane takes PAIRS of consecutive samples
+// and writes each coordinate row with one 16-byte store (st.global.v2.f64) when the rows are 16-byte aligned (even
+// capacity), so a warp writes 512 contiguous bytes per coordinate and instruction.
 template <int MODE, int RTH, int D, int ORD>
 __global__ void __launch_bounds__(256) tg_sample_kernel(const SampleArgs a)
 {
@@ -150,8 +151,21 @@ __global__ void __launch_bounds__(256) tg_sample_kernel(const SampleArgs a)
             step = num > 1 ? __ddiv_rn(__dsub_rn(last, off), (double)(num - 1)) : 0.0;
         }
         const int kend = num < a.cap ? num : (int)a.cap;
+        const bool vec = (a.cap & 1) == 0 && (reinterpret_cast<size_t>(a.out) & 15) == 0;
+        double *orow = a.out + ((long)b * D) * (long)a.cap;
 #pragma unroll 2
-        for (int k = k0 + lane; k < k0 + 256 && k < kend; k += 32) tg_sample_one<MODE, RTH, D, ORD>(a, b, k, P, sf, kd, num, step, off, last);
+        for (int k = k0 + 2 * lane; k < k0 + 256 && k < kend; k += 64) {
+            double v0[D], v1[D];
+            tg_sample_one<MODE, RTH, D, ORD>(a, b, k, P, sf, kd, num, step, off, last, v0);
+            const bool two = k + 1 < kend;
+            if (two) tg_sample_one<MODE, RTH, D, ORD>(a, b, k + 1, P, sf, kd, num, step, off, last, v1);
+#pragma unroll
+            for (int c = 0; c < D; c++) {
+                double *o = orow + (long)c * a.cap + k;
+                if (vec && two) *reinterpret_cast<double2 *>(o) = make_double2(v0[c], v1[c]);
+                else { o[0] = v0[c]; if (two) o[1] = v1[c]; }
+            }
+        }
     }
 }
 

@@ -99,6 +99,7 @@ TG_HD void tg_sqp_carve4(const TgLayout &L, double *prefix, double *pbase, doubl
     w.ctl = (TgSqpCtl *)base; o += TG_CTL_DOUBLES;
     TG_TAKE(x, n1); TG_TAKE(xl, n1); TG_TAKE(xu, n1); TG_TAKE(g, n1); TG_TAKE(s, n1); TG_TAKE(x0, n1);
     TG_TAKE(c, m + 1); TG_TAKE(mu, m + 1);
+    o += o & 1;                  // even counts: the staged pieces are moved with 16-byte accesses (double2 / 16-byte cp.async)
     if (npre_) *npre_ = o;
     base = pbase;
     TG_TAKE(gl, n1); TG_TAKE(r, w.nc + 1);
@@ -106,7 +107,9 @@ TG_HD void tg_sqp_carve4(const TgLayout &L, double *prefix, double *pbase, doubl
     w.ract = (int *)(base + o); o += (size_t)(n1 / 2 + 1);
     TG_TAKE(rot, L.n_sfc ? L.nint * L.d * L.d : 0);
     TG_TAKE(A, w.lda * n1);
+    o += o & 1;
     TG_TAKE(Lm, n * n);          // last: the lock-step QP kernel stages everything in front of it and leaves L in global memory
+    o += o & 1;
     if (np_) *np_ = o;
     o = 0; base = sbase;
     TG_TAKE(u, n1); TG_TAKE(v, n1); TG_TAKE(w, n1);
@@ -117,6 +120,7 @@ TG_HD void tg_sqp_carve4(const TgLayout &L, double *prefix, double *pbase, doubl
     TG_TAKE(rotq, L.n_sfc ? L.nint * L.d * L.d : 0);
     double *ints = base + o; o += (size_t)((n1 + 1 + w.nc + 1) / 2 + 1);
     w.act = (int *)ints; w.iact = w.act + n1 + 1;
+    o += o & 1;
     if (nsq_) *nsq_ = o;
     if (ebase) { base = ebase - o; }
     TG_TAKE(cf, m + 1); TG_TAKE(scratch, tg_scratch_doubles(L));       // <- all the line-search stage needs
@@ -140,6 +144,9 @@ TG_HD void tg_sqp_carve2(const TgLayout &L, double *pbase, double *sbase, TgSqpW
 TG_HD size_t tg_sqp_ls_scratch_doubles(const TgLayout &L) { return (size_t)L.m + 1 + tg_scratch_doubles(L); }
 TG_HD size_t tg_sqp_qp_scratch_doubles(const TgLayout &L) { size_t a, b, c, d; tg_sqp_carve4(L, 0, 0, 0, 0, 0, &a, &b, &c, &d); return d; }
 TG_HD size_t tg_sqp_prefix_doubles(const TgLayout &L) { size_t a, b, c; tg_sqp_carve3(L, 0, 0, 0, 0, &a, &b, &c); return c; }
+
+// doubles the factor L occupies at the end of the persistent block (n^2 padded to an even count)
+TG_HD size_t tg_sqp_factor_doubles(const TgLayout &L) { const size_t q = (size_t)L.n * L.n; return q + (q & 1); }
 
 TG_HD size_t tg_sqp_persistent_doubles(const TgLayout &L) { size_t a, b; tg_sqp_carve2(L, 0, 0, 0, &a, &b); return a; }
 TG_HD size_t tg_sqp_scratch_doubles(const TgLayout &L) { size_t a, b; tg_sqp_carve2(L, 0, 0, 0, &a, &b); return b; }
