@@ -12,8 +12,8 @@ x0 + k ulp (k = +/-1 .. +/-4: `neighbours`) and the contract is read off those r
   * otherwise, `status_stable` (every reference run ends with the same status): same status; if that status is 0
         the objective lies inside the reference's own range of final objectives (widened by the width of that
         range, nine samples, plus 1e-6 relative = ftol),
-        the solution is as close to the recorded one as the reference's own runs are, and it is feasible to the
-        level the reference's own solutions are (never looser than 1e-6 + theirs);
+        the solution is no further from the recorded one than twice the largest distance among the reference's own
+        runs, and it is feasible to the level the reference's own solutions are (never looser than 1e-6 + theirs);
   * otherwise (the reference's status flag itself flips under 1 ulp): the status is one the reference produced,
         with the same feasibility check when it is 0.
   Iteration-limit exits (status 9) also agree on the iteration count.
@@ -21,6 +21,7 @@ x0 + k ulp (k = +/-1 .. +/-4: `neighbours`) and the contract is read off those r
 import numpy as np
 
 NIT_SLACK = 3        # iterations outside the range of the reference's own nine runs that a stable fixture may take
+SCATTER_FACTOR = 2   # unstable fixtures: distance to the recorded answer <= this x the largest distance among the reference's own runs
 
 
 def check(name, golden_solve, ncp, x, status, nit, f, cons, meq):
@@ -50,7 +51,7 @@ def check(name, golden_solve, ncp, x, status, nit, f, cons, meq):
         tol = (fhi - flo) + 1e-6 * max(abs(flo), abs(fhi), 1.0)
         assert flo - tol <= f <= fhi + tol, ctx + (flo, fhi)
         if s["status"] == 0:
-            assert dcp <= max(1e-5, max(r["dcp"] for r in conv)), ctx
+            assert dcp <= max(1e-5, SCATTER_FACTOR * max(r["dcp"] for r in conv)), ctx
         c = np.asarray(cons(np.asarray(x)))
         eq_ref = max([r["c_max_eq"] for r in conv] + [0.0])
         in_ref = min([r["c_min_ineq"] for r in conv] + [0.0])

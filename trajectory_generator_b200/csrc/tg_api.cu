@@ -690,6 +690,29 @@ static int tg_solve_mixed_impl(bool host, int nbuckets, const int *specs, const 
     const int workers = nbuckets < TG_MIXED_WORKERS ? nbuckets : TG_MIXED_WORKERS;
     for (int w = 0; w < workers; w++)
         if (!g_mixed[w].st) TG_CUDA(cudaStreamCreateWithFlags(&g_mixed[w].st, cudaStreamNonBlocking));
+    // every slot is sized for the largest bucket up front: which worker takes which bucket varies from call to call, and
+    // a slot that had to grow in the middle of a call (cudaFree + cudaMalloc synchronise the device) cost up to 2.5x
+    {
+        size_t ws_max = 0, par_max = 0, x_max = 0, f_max = 0, i_max = 0;
+        for (int k = 0; k < nbuckets; k++) {
+            if (counts[k] <= 0) continue;
+            const int *spec = specs + (size_t)k * TG_SP_COUNT;
+            TgShape S;
+            tg_make_shape(spec, &S);
+            const size_t B = (size_t)counts[k], wsb = tg_solve_workspace_bytes(spec, counts[k]);
+            if (!wsb) return tg_fail(5, g_err[0] ? g_err : "cannot plan the solve kernel");
+            ws_max = wsb > ws_max ? wsb : ws_max;
+            par_max = B * (S.L.P + 1) * sizeof(double) > par_max ? B * (S.L.P + 1) * sizeof(double) : par_max;
+            x_max = B * S.L.n * sizeof(double) > x_max ? B * S.L.n * sizeof(double) : x_max;
+            f_max = B * sizeof(double) > f_max ? B * sizeof(double) : f_max;
+            i_max = B * 3 * sizeof(int) > i_max ? B * 3 * sizeof(int) : i_max;
+        }
+        for (int w = 0; w < workers; w++) {
+            if ((rc = g_mixed[w].ws.ensure(ws_max))) return rc;
+            if (host && ((rc = g_mixed[w].par.ensure(par_max)) || (rc = g_mixed[w].x.ensure(x_max)) ||
+                         (rc = g_mixed[w].f.ensure(f_max)) || (rc = g_mixed[w].i.ensure(i_max)))) return rc;
+        }
+    }
     cudaEvent_t fork = nullptr;
     if (!host) {
         TG_CUDA(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
