@@ -148,22 +148,26 @@ def test_fused_and_lockstep_kernels_agree(native_lib):
         assert (a["status"] == 0).mean() > 0.7
 
 
-@pytest.mark.parametrize("name", ["obstacle2d", "sfc3d", "sfc3d_four"])
-def test_dropin_generate_trajectory_matches_reference(native_lib, name):
+@pytest.mark.parametrize("name", ["obstacle2d", "sfc3d", "sfc3d_four", "obstacles8", "c1_sfc2d"])
+def test_dropin_generate_trajectory_matches_reference(native_lib, oracle_built, name):
     """The reference's public call, through the alias package: TrajectoryGenerator(d).generate_trajectory(container, ...)
-    returns the reference's (control_points[d,N], scale_factor, is_violation) within 1e-5 (fixtures recorded by running
-    the unmodified reference, TG/trajectory_generator.py:65-97)."""
+    returns the reference's (control_points[d,N], scale_factor, is_violation) (fixtures recorded by running the
+    unmodified reference, TG/trajectory_generator.py:65-97) under the contract of tests/parity_contract.py."""
+    import parity_contract
     from trajectory_generation.trajectory_generator import TrajectoryGenerator
     d, cc, kw = problems.ALL[name](helpers.product_namespace())
     s = helpers.load_golden()["problems"][name]["solve"]
+    op = _oracle(name)
     gen = TrajectoryGenerator(d)
     cps, scale, viol = gen.generate_trajectory(cc, **kw)
     ref = np.array(s["control_points"], dtype=float)
     assert cps.shape == ref.shape and cps.dtype == np.float64
-    assert np.abs(cps - ref).max() <= 1e-5
-    assert abs(scale - s["scale_factor"]) <= 1e-5
-    assert bool(viol) == bool(s["is_violation"])
-    assert gen.last_result.status == s["status"] == 0
+    r = gen.last_result
+    assert np.array_equal(cps.flatten(), r.x[:cps.size]) and scale == r.x[cps.size]
+    parity_contract.check(name, s, cps.size + 1, r.x, r.status, r.nit, r.fun, op.cons, op.meq)
+    assert bool(viol) == op.is_violation(r.x, success=r.status == 0)
+    if s["stable"]:
+        assert bool(viol) == bool(s["is_violation"])
 
 
 def test_generate_trajectories_groups_mixed_shapes(native_lib):

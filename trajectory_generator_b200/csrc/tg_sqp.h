@@ -66,6 +66,8 @@ TG_HD int tg_rp(int j) { return j * (j + 1) / 2; }      // offset of column j of
 #ifndef TG_UNROLL_N
 #define TG_UNROLL_N 4
 #endif
+// (Two interleaved accumulator chains per inner product -- even / odd terms, added at the end -- were measured in round 2:
+// QP stage +-0 % on C3 / C4, +3 ... 5 % on C2 / C5: the chains are not what the stage waits on once the loads are counted.)
 #define TG_PRAGMA_(x) _Pragma(#x)
 #define TG_PRAGMA(x) TG_PRAGMA_(x)
 #define TG_UNROLL_INNER TG_PRAGMA(unroll TG_UNROLL_N)
