@@ -21,5 +21,19 @@ for table, default, mode in ((path_problems.ALL, "minimal_velocity_path", True),
         for fd in (True, False):
             r = hs.solve(pp, fd=fd, maxiter=40)
         hs.eval(pp, pp.x0)
+        hs.fd_derivatives(pp, pp.x0)
         print("%-5s %-28s clean (status %d, %d iterations)" % ("path" if mode else "traj", name, r["status"], r["nit"]))
+# the spline order converter (csrc/tg_smooth.h)
+import ctypes, numpy as np
+import tg_oracle_smoothing as osm
+ND = np.ctypeslib.ndpointer(dtype=np.float64, flags="C")
+hs.lib.hs_smooth_solve.argtypes = [ctypes.c_int] * 4 + [ctypes.c_double, ND, ND, ND, np.ctypeslib.ndpointer(dtype=np.int32, flags="C")]
+hs.lib.hs_smooth_initial.argtypes = [ctypes.c_int, ND, ctypes.c_int, ctypes.c_int, ND]
+for name, g in helpers.load_golden("smoothing.json")["cases"].items():
+    cp = np.array(g["cp"], dtype=float)
+    prob = osm.SmoothingProblem(g["new_order"], cp, g["scale"], g["old_order"], g["resolution"])
+    x0 = np.zeros((prob.d, prob.N)); hs.lib.hs_smooth_initial(prob.d, np.ascontiguousarray(cp), cp.shape[1], prob.N, x0)
+    x = x0.flatten().copy(); f = np.zeros(1); nit = np.zeros(1, np.int32)
+    st = hs.lib.hs_smooth_solve(prob.d, prob.N, prob.k, g["resolution"], prob.scale, np.concatenate([prob.Y.flatten(), prob.b.flatten()]), x, f, nit)
+    print("smooth %-26s clean (status %d, %d iterations)" % (name, st, nit[0]))
 PY

@@ -15,10 +15,11 @@ def main():
     from trajectory_generator_b200 import synthetic as syn
     name = sys.argv[1]; sample = int(sys.argv[2])
     base = hostsim_loader.load(); var = hostsim_loader.HostSim(sys.argv[3] if len(sys.argv) > 3 else '/tmp/dot2_hostsim.so')
-    bt = syn.make(name, syn.FULL_BATCH[name] if False else 4096); L = bt.layout
-    t=time.time()
-    dt, res, kind = bench.run_cpu_sample(name, 4096, sample, 8)
-    dt2, res2, _ = bench.run_cpu_sample(name, 4096, sample, 8, perturb=True)
+    bt = syn.make(name, 4096); L = bt.layout
+    pool = bench.CpuPool(name, bt.take(range(sample)), os.cpu_count() or 1)
+    dt, res = pool.run()
+    dt2, res2 = pool.run(perturb=1)
+    pool.close()
     print("reference solves: %.1f s + %.1f s" % (dt, dt2))
     st_ref = np.array([r[1] for r in res]); x_ref = np.array([r[4] for r in res])
     st2 = np.array([r[1] for r in res2]); x2 = np.array([r[4] for r in res2])
