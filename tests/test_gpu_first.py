@@ -186,6 +186,20 @@ def test_generate_trajectories_groups_mixed_shapes(native_lib):
         assert np.array_equal(res.control_points, one[0]) and res.scale_factor == one[1]
 
 
+def test_generate_trajectories_pipelines_long_lists(native_lib):
+    """More than two chunks of containers: packing of the next chunk overlaps the solve of the current one; every
+    container's answer is bit for bit what the array-level call gives for the same problem."""
+    from trajectory_generator_b200 import batch, synthetic as syn
+    from trajectory_generator_b200.trajectory_generator import TrajectoryGenerator
+    b = syn.make("C2", 2 * TrajectoryGenerator.PIPELINE_CHUNK + 300)
+    ccs = [syn.container_for(b, i)[1] for i in range(len(b))]
+    res = TrajectoryGenerator(2).generate_trajectories(ccs)
+    ref = batch.solve_host(b.spec, b.par, b.x0, jacobian="fd")
+    assert len(res) == len(b)
+    assert np.array_equal(np.stack([r.x for r in res]), ref["x"])
+    assert [r.status for r in res] == ref["status"].tolist() and [r.nit for r in res] == ref["nit"].tolist()
+
+
 def test_results_do_not_depend_on_batch_size_or_position(native_lib):
     """Problems are independent: a problem's answer is bit for bit the same alone, in a ragged batch (sizes that are not
     multiples of the lane-group / CTA granularity) or behind other problems, in both Jacobian modes; an empty batch is

@@ -110,6 +110,28 @@ TG_HD double tg_wsum(double v)
     return v;
 }
 
+// two sums at once: same folds, but a 64-lane group exchanges both partial sums through shared memory behind ONE pair of
+// named barriers instead of two
+TG_HD void tg_wsum2(double &a, double &b)
+{
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+    for (int o = (TG_GS > 32 ? 32 : TG_GS) / 2; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(TG_GMASK(), a, o);
+        b += __shfl_xor_sync(TG_GMASK(), b, o);
+    }
+#if TG_GS == 64
+    __shared__ double slot[TG_MAX_CTA_GROUPS64][2][2];
+    const int g = threadIdx.x >> 6;
+    if ((threadIdx.x & 31) == 0) { slot[g][(threadIdx.x >> 5) & 1][0] = a; slot[g][(threadIdx.x >> 5) & 1][1] = b; }
+    TG_SYNC();
+    a = slot[g][0][0] + slot[g][1][0];
+    b = slot[g][0][1] + slot[g][1][1];
+    TG_SYNC();
+#endif
+#endif
+}
+
 // larger value wins; ties -> smaller index (the reference scans upward with a strict '>')
 TG_HD void tg_wargmax(double &v, int &i)
 {

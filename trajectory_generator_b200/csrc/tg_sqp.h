@@ -392,8 +392,8 @@ TG_QFN void tg_qp_directions(const TgSqpWs &W, int nq, int iq, double &d2n, doub
         if (k >= iq) a += h * h;
         b += h * h;
     }
-    d2n = tg_wsum(a);
-    dn = tg_wsum(b);
+    tg_wsum2(a, b);
+    d2n = a; dn = b;
     TG_SYNC();
     // (64-lane groups: forming z on the second warp while the first runs the back substitution below was measured
     // neutral, +-0.5 %)
@@ -959,7 +959,7 @@ TG_QFN void tg_sqp_stage_qp(const TgLayout &L, const TgSqpWs &W)
             h1 = 0; h2 = 0;
             #pragma unroll 1
             for (int i = lane; i < n; i += TG_NL) { h1 += W.s[i] * W.u[i]; h2 += W.s[i] * W.v[i]; }
-            h1 = tg_wsum(h1); h2 = tg_wsum(h2);
+            tg_wsum2(h1, h2);
             h3 = 0.2 * h2;
             if (h1 < h3) {
                 const double h4 = (h2 - h3) / (h2 - h1);

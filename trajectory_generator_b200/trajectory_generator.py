@@ -11,7 +11,7 @@ import numpy as np
 from . import batch
 from .constraint_data_structures.constraints_container import ConstraintsContainer
 from .constraint_data_structures.waypoint_data import Waypoint
-from .problem import pack_problem, pack_problems
+from .problem import PackedGroup, pack_problem, pack_problems
 
 
 class TrajectoryResult:
@@ -65,36 +65,57 @@ class TrajectoryGenerator:
     def generate_trajectories(self, containers, objective_function_type="minimal_velocity_and_time_path",
                               num_intervals_free_space=None, initial_control_points=None, initial_scale_factors=None):
         """Solves every container; problems of identical shape share one kernel launch.
-        Returns a list of TrajectoryResult in input order."""
+        Returns a list of TrajectoryResult in input order.  Long lists go through in chunks of PIPELINE_CHUNK
+        containers: a helper thread packs the next chunk while the GPU solves the current one (the library call
+        releases the GIL), so the Python-side packing is hidden behind the solve or the other way round."""
         count = len(containers)
         results = [None] * count
-        if initial_control_points is None and initial_scale_factors is None:
+        default_guess = initial_control_points is None and initial_scale_factors is None
+        if default_guess and count > 2 * self.PIPELINE_CHUNK:
+            from concurrent.futures import ThreadPoolExecutor
+            bounds = list(range(0, count, self.PIPELINE_CHUNK)) + [count]
+            pack = lambda a, b: pack_problems(self._dimension, containers[a:b], objective_function_type, num_intervals_free_space)
+            with ThreadPoolExecutor(max_workers=1) as pool:
+                pending = pool.submit(pack, bounds[0], bounds[1])
+                for k in range(len(bounds) - 1):
+                    groups = pending.result()
+                    if k + 2 < len(bounds):
+                        pending = pool.submit(pack, bounds[k + 1], bounds[k + 2])
+                    self._solve_groups(groups, results, bounds[k])
+            return results
+        if default_guess:
             # vectorised packing: containers grouped by shape, one numpy gather per field (problem.pack_problems)
-            groups = pack_problems(self._dimension, containers, objective_function_type, num_intervals_free_space)
-            order = [g.indices for g in groups]
-            layouts = [g.layout for g in groups]
-            buckets = [(g.spec, g.par, g.x0) for g in groups]
-        else:
-            icps = initial_control_points if initial_control_points is not None else [None] * count
-            isfs = initial_scale_factors if initial_scale_factors is not None else [None] * count
-            packed = [pack_problem(self._dimension, cc, objective_function_type, num_intervals_free_space, icps[i], isfs[i])
-                      for i, cc in enumerate(containers)]
-            by_key = {}
-            for i, p in enumerate(packed):
-                by_key.setdefault(p.key, []).append(i)
-            order = list(by_key.values())
-            layouts = [packed[idx[0]].layout for idx in order]
-            buckets = [(packed[idx[0]].spec, np.stack([packed[i].par for i in idx]),
-                        np.stack([np.clip(packed[i].x0, packed[i].xl, packed[i].xu) for i in idx])) for idx in order]
+            self._solve_groups(pack_problems(self._dimension, containers, objective_function_type, num_intervals_free_space),
+                               results, 0)
+            return results
+        icps = initial_control_points if initial_control_points is not None else [None] * count
+        isfs = initial_scale_factors if initial_scale_factors is not None else [None] * count
+        packed = [pack_problem(self._dimension, cc, objective_function_type, num_intervals_free_space, icps[i], isfs[i])
+                  for i, cc in enumerate(containers)]
+        by_key = {}
+        for i, p in enumerate(packed):
+            by_key.setdefault(p.key, []).append(i)
+        groups = [PackedGroup(np.asarray(idx), packed[idx[0]].spec, np.stack([packed[i].par for i in idx]),
+                              np.stack([np.clip(packed[i].x0, packed[i].xl, packed[i].xu) for i in idx]),
+                              packed[idx[0]].xl, packed[idx[0]].xu) for idx in by_key.values()]
+        self._solve_groups(groups, results, 0)
+        return results
+
+    PIPELINE_CHUNK = 4096
+
+    def _solve_groups(self, groups, results, offset):
+        """one library call for the groups (shapes) of a chunk; results[offset + index] are filled in"""
+        buckets = [(g.spec, g.par, g.x0) for g in groups]
         if len(buckets) == 1:
             outs = [batch.solve_host(*buckets[0], self._maxiter, self._ftol, self._jacobian)]
         else:       # different shapes: one call, the buckets' solves overlap on the device (tg_solve_mixed_host)
             outs = batch.solve_mixed_host(buckets, self._maxiter, self._ftol, self._jacobian)
-        for idx, lay, out in zip(order, layouts, outs):
+        for g, out in zip(groups, outs):
+            lay, idx = g.layout, g.indices
             xs = out["x"]
             cps_all = xs[:, :lay.d * lay.N].reshape(len(idx), lay.d, lay.N).copy()
             scales = xs[:, lay.ia].tolist(); viol = out["violation"].tolist(); status = out["status"].tolist()
             nit = out["nit"].tolist(); fs = out["f"].tolist()
-            for k, i in enumerate(idx):
-                results[i] = TrajectoryResult(cps_all[k], scales[k], bool(viol[k]), status[k], nit[k], fs[k], xs[k])
+            for k, i in enumerate(idx.tolist()):
+                results[offset + i] = TrajectoryResult(cps_all[k], scales[k], bool(viol[k]), status[k], nit[k], fs[k], xs[k])
         return results
