@@ -191,9 +191,11 @@ def test_generate_trajectories_pipelines_long_lists(native_lib):
     container's answer is bit for bit what the array-level call gives for the same problem."""
     from trajectory_generator_b200 import batch, synthetic as syn
     from trajectory_generator_b200.trajectory_generator import TrajectoryGenerator
-    b = syn.make("C2", 2 * TrajectoryGenerator.PIPELINE_CHUNK + 300)
+    gen = TrajectoryGenerator(2)
+    gen.PIPELINE_CHUNK = 700          # (the default, 32768, would need a list of > 65,536 containers)
+    b = syn.make("C2", 2 * gen.PIPELINE_CHUNK + 300)
     ccs = [syn.container_for(b, i)[1] for i in range(len(b))]
-    res = TrajectoryGenerator(2).generate_trajectories(ccs)
+    res = gen.generate_trajectories(ccs)
     ref = batch.solve_host(b.spec, b.par, b.x0, jacobian="fd")
     assert len(res) == len(b)
     assert np.array_equal(np.stack([r.x for r in res]), ref["x"])

@@ -101,7 +101,9 @@ class TrajectoryGenerator:
         self._solve_groups(groups, results, 0)
         return results
 
-    PIPELINE_CHUNK = 4096
+    # a solve has a fixed latency of ~100 lock-step rounds whatever its size (C2: ~50 ms), so chunks must be large for the
+    # overlap to pay: lists of up to two chunks go through in one piece
+    PIPELINE_CHUNK = 32768
 
     def _solve_groups(self, groups, results, offset):
         """one library call for the groups (shapes) of a chunk; results[offset + index] are filled in"""
