@@ -148,7 +148,7 @@ int tg_sfc_intervals_batch(int d, int ncorr, int B, const double *points, int mi
  * matched at both ends, solved with the batched SLSQP iteration (finite-difference gradient as scipy forms it).
  *   par[b] = [Y (d x resolution: samples of the old spline) | b (d x 6: old position at t0, t1, velocity, acceleration)]
  *   x: in = initial control points (tg_smooth_initial_batch: the arc-length walk of create_initial_control_points,
- *      :83-112; scratch = B * oldN doubles), out = solution.  d * N <= 62.  Device pointers.
+ *      :83-112; scratch = B * oldN doubles), out = solution.  d * N <= 160.  Device pointers.
  */
 size_t tg_smooth_workspace_bytes(int d, int N, int order, int resolution, int B);
 int tg_smooth_batch(int d, int N, int order, int resolution, double scale, int B, const double *par, double *x,

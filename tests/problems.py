@@ -187,15 +187,22 @@ def distance_time2d(ns):
     return d, cc, dict(objective_function_type="minimal_distance_and_time_path")
 
 
+def long2d(ns):
+    """Coverage problem: more than 63 variables (2-D, num_intervals_free_space = 30 -> 33 control points, n = 67): the
+    QP stage's lane-strided loops take two passes and its recurrences the shared-memory form."""
+    d, cc, kw = obstacle2d(ns)
+    return d, cc, dict(num_intervals_free_space=30)
+
+
 ALL = dict(c1_sfc2d=c1_sfc2d, c1_curvature=c1_curvature, obstacle2d=obstacle2d, obstacles8=obstacles8,
            intermediate_waypoints=intermediate_waypoints, intermediate_curvature=intermediate_curvature,
            sfc3d=sfc3d, sfc3d_four=sfc3d_four, sfc_obstacles3d=sfc_obstacles3d, bicycle3=bicycle3, unicycle2=unicycle2,
            bicycle_tangential=bicycle_tangential, features3d=features3d, features2d=features2d,
-           distance_time2d=distance_time2d)
+           distance_time2d=distance_time2d, long2d=long2d)
 
 # problems whose reference solve finishes in a few seconds (solve results are recorded for these)
 SOLVE = ("c1_sfc2d", "c1_curvature", "obstacle2d", "obstacles8", "sfc3d", "sfc3d_four", "sfc_obstacles3d", "bicycle3",
-         "unicycle2", "intermediate_waypoints", "distance_time2d")
+         "unicycle2", "intermediate_waypoints", "distance_time2d", "long2d")
 
 
 def test_point(x0, d, N, seed):

@@ -450,7 +450,8 @@ extern "C" int tg_solve_batch(const int *spec, int B, const double *par, double 
     if (rc) return rc;
     if (B <= 0) return 0;
     if ((rc = tg_plan_solve(S, B, &P))) return rc;
-    if (S.L.n > 62) return tg_fail(3, "more than 62 optimisation variables are not supported by the solve kernel");
+    // (shapes with more than 63 variables run the 64-lane QP kernel with two passes per lane-strided loop; the limit is the
+    // shared memory of the QP stage, checked by tg_plan_solve)
     const size_t phased = P.phased_bytes + tg_lists_bytes(P.chunk);
     const size_t need = (P.global_bytes > phased ? P.global_bytes : phased) + TG_HEADER_BYTES;
     if (!workspace || workspace_bytes < need) return tg_fail(4, "workspace too small (see tg_solve_workspace_bytes)");

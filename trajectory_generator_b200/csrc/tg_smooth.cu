@@ -9,6 +9,8 @@
 
 void tg_note_launch(int count);      // tg_api.cu
 
+#define TG_SMOOTH_MAX_VARIABLES 160      // one warp per spline, workspace in global memory: a practical bound, not a structural one
+
 namespace {
 
 __global__ void tg_smooth_table_kernel(const TgSmoothShape S, double *tab)
@@ -45,7 +47,7 @@ __global__ void tg_smooth_initial_kernel(int d, int oldN, int N, int B, const do
 int tg_smooth_check(int d, int N, int order, int resolution)
 {
     if ((d != 2 && d != 3) || order < 2 || order > TG_SMOOTH_MAX_ORDER || N < order + 1 || resolution < 2) return 2;
-    if (d * N > 62) return 3;          // the SQP stages keep at most 62 variables per problem
+    if (d * N > TG_SMOOTH_MAX_VARIABLES) return 3;
     return 0;
 }
 

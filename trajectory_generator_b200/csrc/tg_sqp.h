@@ -226,8 +226,18 @@ TG_QFN void tg_ldl_update(int n, double sigma, double *z, double *Lm, double *Dd
     TG_SYNC();
 #if defined(__CUDA_ARCH__) && TG_GS >= 32
     // one warp, v in registers (entries lane and lane + 32), the pivot handed round with a shuffle (see the back
-    // substitution of tg_qp_directions); same operations in the same order
-    if (TG_SERIAL_ACTIVE()) {
+    // substitution of tg_qp_directions); same operations in the same order.  n > 64: the shared-memory form.
+    if (n > 64) {
+        if (TG_SERIAL_ACTIVE()) {
+            #pragma unroll 1
+            for (int i = 0; i < n - 1; i++) {
+                const double vv = vf[i];
+                #pragma unroll 1
+                for (int j = i + 1 + lane; j < n; j += TG_SERIAL_LANES) vf[j] -= vv * Lm[i * n + j];
+                TG_SERIAL_SYNC();
+            }
+        }
+    } else if (TG_SERIAL_ACTIVE()) {
         const int l32 = lane & 31;
         double v0 = l32 < n ? vf[l32] : 0.0, v1 = l32 + 32 < n ? vf[l32 + 32] : 0.0;
         #pragma unroll 2
@@ -408,7 +418,19 @@ TG_QFN void tg_qp_directions(const TgSqpWs &W, int nq, int iq, double &d2n, doub
 #if defined(__CUDA_ARCH__) && TG_GS >= 32
     // One warp, the running right-hand side in registers (entries lane and lane + 32), the pivot handed round with
     // a shuffle: no shared-memory round trip and no warp sync per step.  Same operations in the same order.
-    if (TG_SERIAL_ACTIVE()) {
+    // (More than 64 active constraints -- shapes with more than 63 variables: the shared-memory form below.)
+    if (iq > 64) {
+        if (TG_SERIAL_ACTIVE()) {
+            #pragma unroll 1
+            for (int j = iq - 1; j >= 0; j--) {
+                const double rj = W.hw[j] * W.rdi[j];
+                if (lane == 0) W.rq[j] = rj;
+                #pragma unroll 1
+                for (int k = lane; k < j; k += TG_SERIAL_LANES) W.hw[k] -= W.R[tg_rp(j) + k] * rj;
+                TG_SERIAL_SYNC();
+            }
+        }
+    } else if (TG_SERIAL_ACTIVE()) {
         const int l32 = lane & 31;
         double h0 = l32 < iq ? W.hw[l32] : 0.0, h1 = l32 + 32 < iq ? W.hw[l32 + 32] : 0.0;
         #pragma unroll 2

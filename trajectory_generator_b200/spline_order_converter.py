@@ -68,7 +68,7 @@ class SmoothingSpline:
         with torch.cuda.device(dev):
             nbytes = lib.tg_smooth_workspace_bytes(d, N, k, R, B)
             if nbytes == 0:
-                raise RuntimeError("spline order converter: unsupported shape (d * N = %d variables; at most 62; order 2..5)" % (d * N))
+                raise RuntimeError("spline order converter: unsupported shape (d * N = %d variables; at most 160; order 2..5)" % (d * N))
             ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
             f = torch.empty(B, dtype=torch.float64, device=dev)
             status = torch.empty(B, dtype=torch.int32, device=dev)
