@@ -113,5 +113,13 @@ def test_smoothing_batch_equals_one_at_a_time(native_lib):
     for i in (0, 4, 8):
         one, s1 = sm.generate_new_control_points(olds[i], 1.0, 3)
         assert np.array_equal(one, Q[i]) and s1 == scale[i]
+    # 3 x 30 = 90 variables (more than a 64-lane pass): solved; end-point rows satisfied
+    old = np.cumsum(rng.normal(size=(3, 14)), 1)
+    sm3 = SmoothingSpline(3, 3, 50)
+    Q3, s3 = sm3.generate_new_control_points(old, 1.0, 3)
+    prob = osm.SmoothingProblem(3, old, 1.0, 3, 50)
+    assert Q3.shape == (3, 30) and int(sm3.last_result["status"][0]) in (0, 9)
+    assert np.abs(prob.constraints(Q3.flatten())).max() <= 1e-6
+    assert prob.objective(Q3.flatten()) <= prob.objective(prob.x0.flatten())
     with pytest.raises(RuntimeError, match="unsupported shape"):
-        SmoothingSpline(3, 3, 50).generate_new_control_points(rng.normal(size=(3, 14)), 1.0, 3)      # 3 x 30 variables
+        SmoothingSpline(3, 3, 50).generate_new_control_points(np.cumsum(rng.normal(size=(3, 30)), 1), 1.0, 3)      # 3 x 70 variables
