@@ -213,7 +213,7 @@ static int tg_plan_solve(const TgShape &S, int B, TgSolvePlan *P)
     // lane-strided loop takes one pass.  Persistent state staged through shared memory when 16 problems still fit.
     {
         const char *v = getenv("TG_QP_GS");
-        gs = v ? atoi(v) : (S.L.n + 1 > 32 ? 64 : 32);
+        gs = v ? atoi(v) : (tg_sqp_qp_dim(S.L) > 32 ? 64 : 32);
         if (!(gs == 8 || gs == 16 || gs == 32 || gs == 64)) gs = 32;
     }
     P->gs_qp = gs;

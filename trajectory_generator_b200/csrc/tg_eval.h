@@ -93,6 +93,9 @@
 // ---------------------------------------------------------------------------
 // group folds (identity on the host build)
 // ---------------------------------------------------------------------------
+// (The folds as functions of their own -- one copy each instead of ~100 inlined copies of 10 .. 20 shuffles -- were
+// measured on the 32-lane QP kernels, whose warps wait on instruction fetch: QP stage +6 ... 8 %, the calls cost more
+// than the fetches they save.)
 TG_HD double tg_wsum(double v)
 {
 #if defined(__CUDA_ARCH__)
@@ -561,6 +564,24 @@ TG_HD double tg_minvo_py(int l, int k)
     if (k == 0) return l == 0 ? 1.0 / 6.0 : l == 1 ? 2.0 / 3.0 : l == 2 ? 1.0 / 6.0 : 0.0;
     if (k == 3) return l == 0 ? 0.0 : l == 1 ? 1.0 / 6.0 : l == 2 ? 2.0 / 3.0 : 1.0 / 6.0;
     return tg_minvo(l, k);
+}
+
+// the same 16 numbers as a table, [l][k] (one load instead of a tree of selects: the QP stage regenerates corridor
+// normals from them in several places and its instruction footprint is what its warps wait on)
+#define TG_MV_ROW(l) {tg_minvo_py_c(l, 0), tg_minvo_py_c(l, 1), tg_minvo_py_c(l, 2), tg_minvo_py_c(l, 3)}
+#define tg_minvo_py_c(l, k) ((k) == 0 ? ((l) == 0 ? 1.0 / 6.0 : (l) == 1 ? 2.0 / 3.0 : (l) == 2 ? 1.0 / 6.0 : 0.0) : \
+                             (k) == 3 ? ((l) == 0 ? 0.0 : (l) == 1 ? 1.0 / 6.0 : (l) == 2 ? 2.0 / 3.0 : 1.0 / 6.0) : \
+                             (((l) < 2 ? (l) : 3 - (l)) == 0 ? (((l) < 2 ? (k) : 3 - (k)) == 1 ? TG_MVB : TG_MVC) : (((l) < 2 ? (k) : 3 - (k)) == 1 ? TG_MVF : TG_MVG)))
+#ifdef __CUDACC__
+static __device__ const double tg_minvo_py_dev[4][4] = {TG_MV_ROW(0), TG_MV_ROW(1), TG_MV_ROW(2), TG_MV_ROW(3)};
+#endif
+TG_HD double tg_minvo_py_t(int l, int k)
+{
+#ifdef __CUDA_ARCH__
+    return tg_minvo_py_dev[l][k];
+#else
+    return tg_minvo_py(l, k);
+#endif
 }
 
 // ---- signed clearance of interval j's MINVO hull to a sphere,

@@ -4,5 +4,5 @@
 #define TG_QP_ONLY
 #define TG_SFX _g64
 // fixed shapes (tg_shape.h) with instantiations in this translation unit: the BASELINE configurations this group size serves
-#define TG_QP_FIXED TG_FIXED_CASE(TG_FIX_C3) TG_FIXED_CASE(TG_FIX_C4)
+#define TG_QP_FIXED TG_FIXED_CASE(TG_FIX_C3)
 #include "tg_kernels_solve.inc"

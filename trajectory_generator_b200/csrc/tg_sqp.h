@@ -48,6 +48,10 @@ enum { TG_ST_INIT = 0, TG_ST_QP, TG_ST_LS, TG_ST_UPDATE, TG_ST_DONE };
 struct TgSqpWs {
     int n, n1, m, lda, ldq, nc;      // nc = m + 2*n1 (constraints incl. variable bounds); lda: rows of A (no corridor rows)
     int sfc0, nsfc, sfc_npts, cpN, cpd;      // corridor rows [sfc0, sfc0 + 2 nsfc): row -> interval -> the only non-zero columns
+    // variables pinned by an equality row with a single entry (zero-velocity terminal waypoints pin three control
+    // points per coordinate, CF/waypoint_constraints.py:122-147): eliminated from the QP subproblem, see tg_qp_solve.
+    // ne of them (nf = n - ne stay); esk / eek: pins at the start / at the end; erow_s / erow_e: first pin row of each
+    int ne, nf, esk, eek, erow_s, erow_e;
     TgSqpCtl *ctl;
     // persistent
     double *x, *xl, *xu, *g, *s, *x0, *gl, *c, *mu, *r, *Lm, *Dd, *A;
@@ -57,9 +61,27 @@ struct TgSqpWs {
     double *rotq;        // scratch: copy of rot for the violation scans of the QP stage
     int *act, *iact;
     int *ract;           // persistent: active rows of the last QP, in the order they were added
+    int *perm;           // scratch: QP order (free variables first, pinned ones behind them) -> index of the variable in x
+    double *sq;          // scratch (pinned variables only): the step in QP order, for the factor update
+    double *usc;         // scratch of the factor update (5 n doubles) while the copy of L occupies J's storage
+    int jsz;             // doubles of J's storage
 };
 
 TG_HD int tg_odd(int v) { return v | 1; }
+
+// number of variables the QP subproblem eliminates (pinned control points): 3 d per zero-velocity terminal waypoint
+TG_HD int tg_sqp_pinned(const TgLayout &L)
+{
+#ifdef TG_NO_ELIM
+    return 0;
+#else
+    const int sk = L.n_start == 3 * L.d, ek = L.n_end == 3 * L.d;
+    if (L.d < 1 || L.N < 6) return 0;
+    return 3 * L.d * (sk + ek);
+#endif
+}
+// variables of the (augmented) QP subproblem after the elimination: what the lanes of a group stride over
+TG_HD int tg_sqp_qp_dim(const TgLayout &L) { return L.n - tg_sqp_pinned(L) + 1; }
 TG_HD int tg_rp(int j) { return j * (j + 1) / 2; }      // offset of column j of the packed upper-triangular R
 
 // unroll factor of the sequential inner products / updates of the QP stage (trip counts are n <= 62)
@@ -95,6 +117,10 @@ TG_HD void tg_sqp_carve4(const TgLayout &L, double *prefix, double *pbase, doubl
     const int ma = m - 2 * L.n_sfc;       // rows stored in A
     w.n = n; w.n1 = n1; w.m = m; w.lda = tg_odd(ma > 0 ? ma : 1); w.ldq = tg_odd(n1); w.nc = m + 2 * n1;
     w.sfc0 = L.r_sfcl; w.nsfc = L.n_sfc; w.sfc_npts = 4 * L.nint; w.cpN = L.N; w.cpd = L.d;
+    w.ne = tg_sqp_pinned(L); w.nf = n - w.ne;
+    w.esk = w.ne && L.n_start == 3 * L.d; w.eek = w.ne && L.n_end == 3 * L.d; w.erow_s = L.r_start; w.erow_e = L.r_end;
+    const int nqm = w.nf + 1;            // largest QP subproblem (augmented)
+    if (w.ne) w.ldq = tg_odd(nqm);
     size_t o = 0;
     double *base = prefix;
 #define TG_TAKE(field, count) w.field = base + o; o += (size_t)(count)
@@ -115,13 +141,28 @@ TG_HD void tg_sqp_carve4(const TgLayout &L, double *prefix, double *pbase, doubl
     if (np_) *np_ = o;
     o = 0; base = sbase;
     TG_TAKE(u, n1); TG_TAKE(v, n1); TG_TAKE(w, n1);
-    TG_TAKE(Jq, w.ldq * n1);
-    TG_TAKE(R, n1 * (n1 + 1) / 2 + 1); TG_TAKE(rsub, n1);      // R packed by columns (column j: rows 0..j at j(j+1)/2), its sub-diagonal during a drop
-    TG_TAKE(z, n1); TG_TAKE(dq, n1); TG_TAKE(rq, n1); TG_TAKE(np, n1); TG_TAKE(uq, n1 + 1); TG_TAKE(xq, n1); TG_TAKE(hw, n1);
+    if (w.ne) { TG_TAKE(sq, n1); o += o & 1; } else w.sq = 0;
+    // J (ldq x nqm) and R.  Pinned variables: the copy of L (n x n) that the factor update works on is larger than
+    // the J of the smaller subproblem: it spans J, R and the five vectors behind them, and the update's 5 n doubles of
+    // scratch come from the vectors behind those (uq .. rotq; the rotation table is copied again afterwards); J grows
+    // by whatever the span lacks.
+    const int rsz = w.ne ? nqm * (nqm + 1) / 2 + 1 : n1 * (n1 + 1) / 2 + 1;
+    const int rotsz = L.n_sfc ? L.nint * L.d * L.d : 0;
+    int jsz = w.ne ? w.ldq * nqm : w.ldq * n1;
+    if (w.ne && jsz + rsz + 5 * n1 < n * n) jsz = n * n - rsz - 5 * n1;
+    const int uscsz = w.ne ? (n1 + 1) + 3 * n1 + rotsz : 0;
+    w.jsz = jsz;
+    TG_TAKE(Jq, jsz);
+    TG_TAKE(R, rsz);
+    TG_TAKE(rsub, n1);      // R packed by columns (column j: rows 0..j at j(j+1)/2), its sub-diagonal during a drop
+    TG_TAKE(z, n1); TG_TAKE(dq, n1); TG_TAKE(rq, n1); TG_TAKE(np, n1);
+    w.usc = w.ne ? base + o : w.R;
+    TG_TAKE(uq, n1 + 1); TG_TAKE(xq, n1); TG_TAKE(hw, n1);
     TG_TAKE(rdi, n1);
-    TG_TAKE(rotq, L.n_sfc ? L.nint * L.d * L.d : 0);
-    double *ints = base + o; o += (size_t)((n1 + 1 + w.nc + 1) / 2 + 1);
-    w.act = (int *)ints; w.iact = w.act + n1 + 1;
+    TG_TAKE(rotq, rotsz);
+    if (w.ne && uscsz < 5 * n) o += (size_t)(5 * n - uscsz);
+    double *ints = base + o; o += (size_t)((n1 + 1 + w.nc + 1 + (w.ne ? n1 : 0)) / 2 + 1);
+    w.act = (int *)ints; w.iact = w.act + n1 + 1; w.perm = w.iact + w.nc + 1;
     o += o & 1;
     if (nsq_) *nsq_ = o;
     if (ebase) { base = ebase - o; }
@@ -186,8 +227,37 @@ TG_HD double tg_sfc_entry(const TgSqpWs &W, const double *rot, int p, int i)
     const int rr = q / npts, idx = q - rr * npts, j = idx >> 2, k = idx & 3;
     const int c = i / N, l = i - c * N - j;
     if (l < 0 || l > 3) return 0.0;
-    const double v = rot[j * D * D + rr * D + c] * tg_minvo_py(l, k);
+    const double v = rot[j * D * D + rr * D + c] * tg_minvo_py_t(l, k);
     return upper ? -v : v;
+}
+
+// ---------------------------------------------------------------------------
+// Pinned variables.  A zero-velocity terminal waypoint pins three control points per coordinate with rows that have a
+// single entry 1 (tg_jac_location, kind 1).  The QP subproblem then fixes the step of such a variable, d_i = -c_i
+// (zero once the pin holds), so the subproblem is solved over the other nf variables only: with the pinned variables
+// LAST in the order the factor L D L' of B is kept in ("QP order"), the factor of the free block is the leading block
+// of L and D.  C4: 34 -> 25 variables, 9 of its 15 equality rows gone, one warp per problem instead of two.
+// ---------------------------------------------------------------------------
+TG_HD bool tg_is_pin_row(const TgSqpWs &W, int p)
+{
+    return (W.esk && p >= W.erow_s && p < W.erow_s + 3 * W.cpd) || (W.eek && p >= W.erow_e && p < W.erow_e + 3 * W.cpd);
+}
+// variable of x -> position in QP order (free variables keep their order; pinned ones follow, ascending)
+TG_HD int tg_qp_index(const TgSqpWs &W, int i)
+{
+    if (!W.ne) return i;
+    const int N = W.cpN, per = 3 * (W.esk + W.eek);
+    if (i >= W.cpd * N) return i - W.cpd * per;
+    const int c = i / N, j = i - c * N;
+    if (W.esk && j < 3) return W.nf + c * per + j;
+    if (W.eek && j >= N - 3) return W.nf + c * per + 3 * W.esk + (j - (N - 3));
+    return i - c * per - 3 * W.esk;
+}
+// pinned variable e (QP position nf + e) -> its row
+TG_HD int tg_pin_row(const TgSqpWs &W, int e)
+{
+    const int per = 3 * (W.esk + W.eek), c = e / per, t = e - c * per;
+    return (W.esk && t < 3) ? W.erow_s + 3 * c + t : W.erow_e + 3 * c + (t - 3 * W.esk);
 }
 
 // coefficient of the slack variable of the augmented problem in row j (SLSQP: -c for equalities, max(-c, 0) else)
@@ -350,10 +420,35 @@ TG_QFN void tg_ldl_apply(int n, const double *Lm, const double *Dd, const double
 // ---------------------------------------------------------------------------
 #define TG_QP_OK 1
 
-TG_HD void tg_qp_normal(const TgSqpWs &W, int nq, int meq, int p, double *np)
+// entry i (a variable of x; i == n: the slack of the augmented problem) of the normal of row / bound p
+TG_HD double tg_normal_entry(const TgSqpWs &W, int meq, int p, int i)
+{
+    if (p < W.m) {
+        if (tg_is_sfc_row(W, p)) return i < W.n ? tg_sfc_entry(W, W.rotq, p, i) : tg_slack_coeff(W, meq, p);
+        return W.A[i * W.lda + tg_arow(W, p)];
+    }
+    const int q = p - W.m;
+    const int i0 = q < W.n1 ? q : q - W.n1;
+    return i == i0 ? (q < W.n1 ? 1.0 : -1.0) : 0.0;
+}
+
+// ELIM: entry k of the QP's vectors belongs to variable perm[k] of x (k < nf) or to the slack (k == nf)
+#define TG_XI(k) (ELIM ? ((k) < W.nf ? W.perm[k] : W.n) : (k))
+
+template <bool ELIM>
+TG_HD void tg_qp_normal(const TgSqpWs &W, int nq, int meq, int p, double *np, bool coupled)
 {
     const int lane = TG_LANE();
-    if (p < W.m && tg_is_sfc_row(W, p)) {
+    if (ELIM) {
+        #pragma unroll 1
+        for (int k = lane; k < nq; k += TG_NL) {
+            double h = tg_normal_entry(W, meq, p, TG_XI(k));
+            if (coupled && k == W.nf)        // the slack moves the pinned variables along c_P (W.w)
+                #pragma unroll 1
+                for (int e = 0; e < W.ne; e++) h += tg_normal_entry(W, meq, p, W.perm[W.nf + e]) * W.w[e];
+            np[k] = h;
+        }
+    } else if (p < W.m && tg_is_sfc_row(W, p)) {
         #pragma unroll 1
         for (int i = lane; i < nq; i += TG_NL) np[i] = i < W.n ? tg_sfc_entry(W, W.rotq, p, i) : tg_slack_coeff(W, meq, p);
     } else if (p < W.m) {
@@ -371,13 +466,23 @@ TG_HD void tg_qp_normal(const TgSqpWs &W, int nq, int meq, int p, double *np)
 }
 
 // value of constraint p at xq (lane-parallel reduction; same result on all lanes).  W.np holds the normal of p
-// (tg_qp_normal): row p of A is not read a second time
-TG_HD double tg_qp_value(const TgSqpWs &W, int nq, int p)
+// (tg_qp_normal): row p of A is not read a second time.  ELIM: xq stays in the order of x; `pins`: some pinned
+// variable has a non-zero step, whose product with the normal's entry is added
+template <bool ELIM>
+TG_HD double tg_qp_value(const TgSqpWs &W, int nq, int meq, int p, bool pins, bool coupled)
 {
     if (p < W.m) {
         double s = 0;
         #pragma unroll 1
-        for (int i = TG_LANE(); i < nq; i += TG_NL) s += W.np[i] * W.xq[i];
+        for (int i = TG_LANE(); i < nq; i += TG_NL) s += W.np[i] * W.xq[TG_XI(i)];
+        if (ELIM && pins) {
+            #pragma unroll 1
+            for (int e = TG_LANE(); e < W.ne; e += TG_NL) {
+                const int i = W.perm[W.nf + e];
+                // (coupled: the slack's share of the pinned steps is part of np[nf]; what is left is -c_P)
+                s += tg_normal_entry(W, meq, p, i) * (coupled ? -W.w[e] : W.xq[i]);
+            }
+        }
         return tg_wsum(s) + W.c[p];
     }
     const int q = p - W.m;
@@ -529,37 +634,133 @@ TG_QFN void tg_qp_drop(const TgSqpWs &W, int nq, int &iq, int l)
     TG_SYNC();
 }
 
-TG_QFN int tg_qp_solve(const TgSqpWs &W, const double *Lsrc, int nq, int meq, double rho, double &fl, int &nract, double dfloor)
+// ELIM (pinned variables, see tg_is_pin_row): nq = nf (+ 1) variables in QP order; W.xq, W.g, W.u, W.v, A keep the
+// order of x.  Lsrc / W.Lm / W.Dd: the factor of B in QP order.
+template <bool ELIM>
+TG_QFN int tg_qp_solve(const TgSqpWs &W, const double *Lsrc, int nq, int meq, double rho, double &fl, int &nract, double dfloor,
+                       bool ident)
 {
-    const int lane = TG_LANE(), n = W.n, ld = W.ldq, m = W.m;
+    const int lane = TG_LANE(), ld = W.ldq, m = W.m;
+    const int n = ELIM ? W.nf : W.n;            // variables of the plain subproblem
+    const int nx = nq > n ? W.n1 : W.n;         // entries of xq (order of x; the slack is entry W.n)
     const int nc = m + 2 * W.n1;
+    bool pins = false;                          // ELIM: some pinned variable still has to move
+    double dslack = rho * rho;                  // ELIM, augmented problem while pins move: the slack's entry of D
+    if (ELIM) {
+        #pragma unroll 1
+        for (int e = lane; e < W.ne; e += TG_NL) {
+            const double cv = W.c[tg_pin_row(W, e)];
+            W.w[e] = cv;
+            if (cv != 0) pins = true;
+        }
+        pins = tg_any(pins);
+    }
+    const bool coupled = ELIM && pins && nq > n;      // the slack's column of J is not a unit vector
+    if (ELIM && pins) {
+        // W.sq = B [0; d_P], d_P = -c_P: what the pinned variables' fixed step adds to the gradient of the free ones
+        // (only until the pins hold -- the first iterations).  `ident`: the factor has just been reset, B = I.
+        // (before the packed copy is made: Lsrc may be the copy of L next to J, and the vectors used are outside it)
+        #pragma unroll 1
+        for (int k = lane; k < W.n; k += TG_NL) { W.hw[k] = k < W.nf ? 0.0 : -W.w[k - W.nf]; if (ident) W.sq[k] = W.hw[k]; }
+        TG_SYNC();
+        if (!ident) tg_ldl_apply(W.n, Lsrc, W.Dd, W.hw, W.rdi, W.sq);
+    }
     const double EPS_DEP = 1e-26;     // |d2|^2 <= EPS_DEP |d|^2 : normal lies in the span of the active ones
     // ---- J = L^-T D^-1/2 (upper triangular), augmented entry 1/rho.  L is read n^2/2 times per lane: copy it next
     //      to J first (the storage of R is free until the first constraint is added)
-    // (packed: row i of the copy holds L[i][j], j > i, at i n - i (i + 1) / 2 - i - 1 + j)
+    // (packed: row i of the copy holds L[i][j], j > i, at i npk - i (i + 1) / 2 - i - 1 + j)
     double *Ls = W.R;
-    #pragma unroll 1
-    for (int i = 0; i < n - 1; i++) {
-        const int bi = i * n - i * (i + 1) / 2 - i - 1;
+    const int npk = coupled ? nq : n;                 // rows of the packed copy (coupled: + the slack's row, below)
+    if (ELIM && Lsrc == W.Jq) {
+        // The copy of L that the factor update left behind spans J's storage, R's and the vectors behind them (tg_sqp_carve4):
+        // its entries that lie in R's storage are set aside first (W.usc: outside the span), then the packed copy is
+        // written.  From here on the span is free; whatever else needs L reads W.Lm.
+        double *tmp = W.usc;
+        int toff = 0;
         #pragma unroll 1
-        for (int j = i + 1 + lane; j < n; j += TG_NL) Ls[bi + j] = Lsrc[i * n + j];
+        for (int i = 0; i < n - 1; i++) {
+            int j0 = W.jsz - i * W.n;
+            if (j0 < i + 1) j0 = i + 1;
+            #pragma unroll 1
+            for (int j = j0 + lane; j < n; j += TG_NL) tmp[toff + j - j0] = Lsrc[i * W.n + j];
+            if (j0 < n) toff += n - j0;
+        }
+        TG_SYNC();
+        toff = 0;
+        #pragma unroll 1
+        for (int i = 0; i < n - 1; i++) {
+            const int bi = i * npk - i * (i + 1) / 2 - i - 1;
+            int j0 = W.jsz - i * W.n;
+            if (j0 < i + 1) j0 = i + 1;
+            #pragma unroll 1
+            for (int j = i + 1 + lane; j < n; j += TG_NL) Ls[bi + j] = j < j0 ? Lsrc[i * W.n + j] : tmp[toff + j - j0];
+            if (j0 < n) toff += n - j0;
+        }
+    } else {
+        #pragma unroll 1
+        for (int i = 0; i < n - 1; i++) {
+            const int bi = i * npk - i * (i + 1) / 2 - i - 1;
+            #pragma unroll 1
+            for (int j = i + 1 + lane; j < n; j += TG_NL) Ls[bi + j] = Lsrc[i * W.n + j];
+        }
     }
     TG_SYNC();
+    if (ELIM) {
+        #pragma unroll 1
+        for (int e = lane; e < W.ne; e += TG_NL) W.xq[W.perm[W.nf + e]] = -W.w[e];
+        #pragma unroll 1
+        for (int k = lane; k < nq; k += TG_NL) W.rq[k] = W.g[TG_XI(k)];       // gradient in QP order
+        TG_SYNC();
+        if (pins) {
+            // g_f + B_fP d_P = g_f + (B [0; d_P])_f
+            #pragma unroll 1
+            for (int k = lane; k < W.nf; k += TG_NL) W.rq[k] += W.sq[k];
+            TG_SYNC();
+            if (coupled) {
+                // Augmented problem: the pin rows read d_P = -(1 - slack) c_P, so the slack moves the pinned variables
+                // along c_P.  In the variables [d_f; slack] the Hessian gains the row [B_fP c_P, c_P' B_PP c_P + rho^2]:
+                // its factor is the free block's plus one row l = L_Pf' c_P with D entry rho^2 + |D_P^1/2 L_PP' c_P|^2,
+                // and the slack's gradient entry is c_P' (g + B [0; d_P])_P.
+                double gsl = 0, dd = 0;
+                #pragma unroll 1
+                for (int e = lane; e < W.ne; e += TG_NL) {
+                    gsl += W.w[e] * (W.g[W.perm[W.nf + e]] + W.sq[W.nf + e]);
+                    double h = W.w[e];
+                    if (!ident)
+                        #pragma unroll 1
+                        for (int e2 = e + 1; e2 < W.ne; e2++) h += W.Lm[(W.nf + e) * W.n + W.nf + e2] * W.w[e2];
+                    dd += W.Dd[W.nf + e] * h * h;
+                }
+                tg_wsum2(gsl, dd);
+                dslack += dd;
+                #pragma unroll 1
+                for (int k = lane; k < W.nf; k += TG_NL) {
+                    double h = 0;
+                    if (!ident)
+                        #pragma unroll 1
+                        for (int e = 0; e < W.ne; e++) h += W.Lm[k * W.n + W.nf + e] * W.w[e];
+                    Ls[k * npk - k * (k + 1) / 2 - k - 1 + W.nf] = h;
+                }
+                if (lane == 0) W.rq[W.nf] += gsl;
+                TG_SYNC();
+            }
+        }
+    }
     #pragma unroll 1
     for (int k = lane; k < nq; k += TG_NL) {
         double *col = W.Jq + k * ld;
         for (int i = 0; i < nq; i++) col[i] = 0;
-        if (k < n) {
+        if (k < n || coupled) {
             col[k] = 1;
             #pragma unroll 1
             for (int i = k - 1; i >= 0; i--) {
                 double h = 0;
-                const double *Li = Ls + (i * n - i * (i + 1) / 2 - i - 1);
+                const double *Li = Ls + (i * npk - i * (i + 1) / 2 - i - 1);
                 TG_UNROLL_INNER
                 for (int j = i + 1; j <= k; j++) h += Li[j] * col[j];
                 col[i] = -h;
             }
-            const double sc = 1 / sqrt(fmax(W.Dd[k], dfloor));
+            const double sc = 1 / sqrt(fmax(k < n ? W.Dd[k] : dslack, dfloor));
             for (int i = 0; i <= k; i++) col[i] *= sc;
         } else col[k] = 1 / rho;      // SLSQP's LSQ puts rho itself (not its root) on the diagonal of E: penalty rho^2/2 delta^2
     }
@@ -571,7 +772,7 @@ TG_QFN int tg_qp_solve(const TgSqpWs &W, const double *Lsrc, int nq, int meq, do
     for (int k = lane; k < nq; k += TG_NL) {
         double h = 0;
         TG_UNROLL_INNER
-        for (int i = 0; i < nq; i++) h += W.Jq[k * ld + i] * W.g[i];
+        for (int i = 0; i < nq; i++) h += W.Jq[k * ld + i] * (ELIM ? W.rq[i] : W.g[i]);
         W.dq[k] = h;
     }
     TG_SYNC();
@@ -580,9 +781,14 @@ TG_QFN int tg_qp_solve(const TgSqpWs &W, const double *Lsrc, int nq, int meq, do
         double h = 0;
         TG_UNROLL_INNER
         for (int k = 0; k < nq; k++) h += W.Jq[k * ld + i] * W.dq[k];
-        W.xq[i] = -h;
+        W.xq[TG_XI(i)] = -h;
     }
     TG_SYNC();
+    if (coupled) {
+        #pragma unroll 1
+        for (int e = lane; e < W.ne; e += TG_NL) W.xq[W.perm[W.nf + e]] = -(1 - W.xq[W.n]) * W.w[e];
+        TG_SYNC();
+    }
     int iq = 0;
     double d2n, dn;
     fl += (double)n * n * n / 3 + 4.0 * nq * nq;          // J = L^-T D^-1/2 ; xq = -J J'g
@@ -592,6 +798,7 @@ TG_QFN int tg_qp_solve(const TgSqpWs &W, const double *Lsrc, int nq, int meq, do
     for (int it = 0; it < itmax + meq; it++) {
         const bool eq = it < meq;
         int ip = it;
+        if (ELIM && eq && tg_is_pin_row(W, it)) continue;
         if (!eq) {
             double best = 0;
             ip = 0x7fffffff;
@@ -602,11 +809,11 @@ TG_QFN int tg_qp_solve(const TgSqpWs &W, const double *Lsrc, int nq, int meq, do
                 // instead of 2 d row products of 4 d terms read from A.  (The row that is picked is re-evaluated from
                 // A by tg_qp_value; the scan only ranks violations.)
                 const int npts = W.sfc_npts, D = W.cpd, N = W.cpN;
-                const double slack = nq > n ? W.xq[n] : 0.0;
+                const double slack = nq > n ? W.xq[W.n] : 0.0;
                 #pragma unroll 1
                 for (int q = lane; q < npts; q += TG_NL) {
                     const int j = q >> 2, k = q & 3;
-                    const double m0 = tg_minvo_py(0, k), m1 = tg_minvo_py(1, k), m2 = tg_minvo_py(2, k), m3 = tg_minvo_py(3, k);
+                    const double m0 = tg_minvo_py_t(0, k), m1 = tg_minvo_py_t(1, k), m2 = tg_minvo_py_t(2, k), m3 = tg_minvo_py_t(3, k);
                     double Q[3], Qa[3];
                     #pragma unroll
                     for (int c = 0; c < 3; c++) {
@@ -619,6 +826,14 @@ TG_QFN int tg_qp_solve(const TgSqpWs &W, const double *Lsrc, int nq, int meq, do
                         }
                     }
                     const double *rot = W.rotq + j * D * D;
+                    // (the right-hand sides of this point's 2 d rows up front: they come from the persistent state,
+                    // which sits in global memory when the kernel does not stage it)
+                    double cpv[6];
+                    #pragma unroll
+                    for (int rr = 0; rr < 3; rr++)
+                        #pragma unroll
+                        for (int side = 0; side < 2; side++)
+                            cpv[2 * rr + side] = rr < D ? W.c[W.sfc0 + side * W.nsfc + rr * npts + q] : 0.0;
                     #pragma unroll
                     for (int rr = 0; rr < 3; rr++) {
                         if (rr >= D) continue;
@@ -630,7 +845,7 @@ TG_QFN int tg_qp_solve(const TgSqpWs &W, const double *Lsrc, int nq, int meq, do
                         for (int side = 0; side < 2; side++) {
                             const int p = W.sfc0 + side * W.nsfc + rr * npts + q;
                             if (W.iact[p]) continue;
-                            const double cp = W.c[p];
+                            const double cp = cpv[2 * rr + side];
                             double h = side ? -sq : sq, sc = fabs(cp) + sa;
                             if (nq > n) { const double t = fmax(-cp, 0.0) * slack; h += t; sc += fabs(t); }
                             const double sv = h + cp;
@@ -650,14 +865,14 @@ TG_QFN int tg_qp_solve(const TgSqpWs &W, const double *Lsrc, int nq, int meq, do
                 if (p < m) {
                     const int pa = t;          // row of A: the corridor rows are not stored
                     double h = 0, sc = fabs(W.c[p]);
-                    #pragma unroll 8
-                    for (int i = 0; i < nq; i++) { const double t = W.A[i * W.lda + pa] * W.xq[i]; h += t; sc += fabs(t); }
+                    #pragma unroll 12
+                    for (int i = 0; i < nx; i++) { const double t = W.A[i * W.lda + pa] * W.xq[i]; h += t; sc += fabs(t); }
                     sv = h + W.c[p];
                     tol = 1e-13 * sc;
                 } else {
                     const int q = p - m;
                     const int i = q < W.n1 ? q : q - W.n1;
-                    if (i >= nq) continue;
+                    if (i >= nx) continue;
                     const double bnd = q < W.n1 ? W.u[i] : W.v[i];
                     if (!tg_finite(bnd)) continue;
                     sv = q < W.n1 ? W.xq[i] - bnd : bnd - W.xq[i];
@@ -677,12 +892,30 @@ TG_QFN int tg_qp_solve(const TgSqpWs &W, const double *Lsrc, int nq, int meq, do
                     if (W.act[k] < m) { if (lane == 0) W.ract[cnt] = W.act[k]; cnt++; }
                 nract = cnt;
                 TG_SYNC();
+                if (ELIM && pins) {
+                    // multipliers of the pin rows, from the pinned variables' entries of B d + g = sum of normals x multipliers
+                    // (B d over all variables, QP order; W.Lm: the solve has overwritten the copy of L next to J)
+                    #pragma unroll 1
+                    for (int k = lane; k < W.n; k += TG_NL) { W.hw[k] = W.xq[W.perm[k]]; if (ident) W.dq[k] = W.hw[k]; }
+                    TG_SYNC();
+                    if (!ident) tg_ldl_apply(W.n, W.Lm, W.Dd, W.hw, W.z, W.dq);
+                    #pragma unroll 1
+                    for (int e = lane; e < W.ne; e += TG_NL) {
+                        const int i = W.perm[W.nf + e];
+                        double h = W.dq[W.nf + e] + W.g[i];
+                        #pragma unroll 1
+                        for (int k = 0; k < iq; k++)
+                            if (W.act[k] < m) h -= tg_normal_entry(W, meq, W.act[k], i) * W.uq[k];
+                        W.r[tg_pin_row(W, e)] = h;
+                    }
+                    TG_SYNC();
+                }
                 return TG_QP_OK;
             }
         }
-        tg_qp_normal(W, nq, meq, ip, W.np);
+        tg_qp_normal<ELIM>(W, nq, meq, ip, W.np, coupled);
         double uip = 0;
-        double sv = tg_qp_value(W, nq, ip);
+        double sv = tg_qp_value<ELIM>(W, nq, meq, ip, pins, coupled);
         #pragma unroll 1
         for (int inner = 0; inner < itmax; inner++) {
             tg_qp_directions(W, nq, iq, d2n, dn);
@@ -709,7 +942,10 @@ TG_QFN int tg_qp_solve(const TgSqpWs &W, const double *Lsrc, int nq, int meq, do
             const bool primal = t2 < INFINITY;
             if (primal)
                 #pragma unroll 1
-                for (int i = lane; i < nq; i += TG_NL) W.xq[i] += t * W.z[i];
+                for (int i = lane; i < nq; i += TG_NL) W.xq[TG_XI(i)] += t * W.z[i];
+            if (primal && coupled)
+                #pragma unroll 1
+                for (int e = lane; e < W.ne; e += TG_NL) W.xq[W.perm[W.nf + e]] += t * W.z[n] * W.w[e];
             TG_SYNC();
             if (primal && t2 <= t1) {
                 if (lane == 0) { W.uq[iq] = uip; W.act[iq] = ip; W.iact[ip] = 1; }
@@ -722,7 +958,7 @@ TG_QFN int tg_qp_solve(const TgSqpWs &W, const double *Lsrc, int nq, int meq, do
             fl += 6.0 * (iq - 1 - l) * (nq + 0.5 * (iq - 1 - l));
             tg_qp_drop(W, nq, iq, l);
             if (primal) {
-                sv = tg_qp_value(W, nq, ip);
+                sv = tg_qp_value<ELIM>(W, nq, meq, ip, pins, coupled);
                 if (inner == itmax - 1) return 3;
             }
         }
@@ -925,6 +1161,24 @@ TG_FN void tg_sqp_stage_der(const TgLayout &L, const int *sp, const double *par,
     TG_SYNC();
 }
 
+// copy of the factor between its home and J's storage; `wide`: 16-byte accesses where both ends allow them
+TG_HD void tg_copy_doubles(double *dst, const double *src, int count, bool wide)
+{
+    const int lane = TG_LANE();
+#ifdef __CUDA_ARCH__
+    if (wide && (count & 1) == 0 && ((((size_t)dst) | ((size_t)src)) & 15) == 0) {
+        double2 *d2 = reinterpret_cast<double2 *>(dst);
+        const double2 *s2 = reinterpret_cast<const double2 *>(src);
+        #pragma unroll 8
+        for (int q = lane; q < count / 2; q += TG_NL) d2[q] = s2[q];
+        return;
+    }
+#endif
+    (void)wide;
+    #pragma unroll 4
+    for (int q = lane; q < count; q += TG_NL) dst[q] = src[q];
+}
+
 // lm_far: the persistent state (W.Lm ...) lives in global memory (lock-step kernel of a shape whose state is not
 // staged in shared memory).  The factor L is then copied once into the storage of J (free until the QP is set up),
 // updated there, written back once and handed to the QP set-up from there, instead of being read five times and
@@ -936,8 +1190,10 @@ template <bool LM_FAR, bool SPLIT_NQ = false>
 TG_QFN void tg_sqp_stage_qp(const TgLayout &L, const TgSqpWs &W)
 {
     // the update's scratch (5 n doubles) comes from R's storage when L sits in J's
-    const bool lm_far = LM_FAR && W.n1 * (W.n1 + 1) / 2 + 1 >= 5 * L.n;
+    const bool lm_far = LM_FAR && (W.ne || W.n1 * (W.n1 + 1) / 2 + 1 >= 5 * L.n);
+    const bool elim = W.ne > 0;          // pinned variables: the factor of B and the update's vectors are in QP order
     bool lcopy = false;      // J's storage holds the current L
+    bool ident = false;      // the factor has been reset in this call: B = I
     const int lane = TG_LANE(), n = L.n, m = L.m, meq = L.meq, n1 = W.n1;
     TgSqpCtl ctl = *W.ctl;
     const double acc = ctl.acc, tol = 10 * ctl.acc;
@@ -947,6 +1203,11 @@ TG_QFN void tg_sqp_stage_qp(const TgLayout &L, const TgSqpWs &W)
         // rotation of the corridor that owns each interval: regenerates corridor normals and serves the violation scans
         #pragma unroll 1
         for (int q = lane; q < (W.sfc_npts >> 2) * W.cpd * W.cpd; q += TG_NL) W.rotq[q] = W.rot[q];
+        TG_SYNC();
+    }
+    if (elim) {
+        #pragma unroll 1
+        for (int i = lane; i < n; i += TG_NL) W.perm[tg_qp_index(W, i)] = i;
         TG_SYNC();
     }
     if (ctl.state == TG_ST_UPDATE) {
@@ -960,27 +1221,44 @@ TG_QFN void tg_sqp_stage_qp(const TgLayout &L, const TgSqpWs &W)
             ctl.status = 0; ctl.state = TG_ST_DONE;
         } else {
             // ---- damped BFGS update of L D L' (derivatives at the new point are already in g, A)
+            if (elim) {
+                // (active rows and their multipliers first, side by side in the QP's scratch: the loop below then waits
+                // on one trip to the persistent state instead of one per active row)
+                #pragma unroll 1
+                for (int k = lane; k < ctl.nract; k += TG_NL) { const int j = W.ract[k]; W.act[k] = j; W.uq[k] = W.r[j]; }
+                TG_SYNC();
+            }
             #pragma unroll 1
             for (int i = lane; i < n; i += TG_NL) {
                 double h = W.g[i];
-                #pragma unroll 2
-                for (int k = 0; k < ctl.nract; k++) {
-                    const int j = W.ract[k];
-                    h -= (tg_is_sfc_row(W, j) ? tg_sfc_entry(W, W.rotq, j, i) : W.A[i * W.lda + tg_arow(W, j)]) * W.r[j];
+                if (elim) {
+                    #pragma unroll 4
+                    for (int k = 0; k < ctl.nract; k++) {
+                        const int j = W.act[k];
+                        h -= (tg_is_sfc_row(W, j) ? tg_sfc_entry(W, W.rotq, j, i) : W.A[i * W.lda + tg_arow(W, j)]) * W.uq[k];
+                    }
+                    const int k = tg_qp_index(W, i);
+                    W.u[k] = h - W.gl[i]; W.sq[k] = W.s[i];
+                } else {
+                    #pragma unroll 2
+                    for (int k = 0; k < ctl.nract; k++) {
+                        const int j = W.ract[k];
+                        h -= (tg_is_sfc_row(W, j) ? tg_sfc_entry(W, W.rotq, j, i) : W.A[i * W.lda + tg_arow(W, j)]) * W.r[j];
+                    }
+                    W.u[i] = h - W.gl[i];
                 }
-                W.u[i] = h - W.gl[i];
             }
+            const double *sq = elim ? W.sq : W.s;         // the step in the order of the factor
             TG_SYNC();
             if (lm_far) {
-                #pragma unroll 4
-                for (int q = lane; q < n * n; q += TG_NL) W.Jq[q] = W.Lm[q];
+                tg_copy_doubles(W.Jq, W.Lm, n * n, elim);
                 TG_SYNC();
                 lcopy = true;
-                tg_ldl_apply(n, W.Jq, W.Dd, W.s, W.w, W.v);
-            } else tg_ldl_apply(n, W.Lm, W.Dd, W.s, W.w, W.v);
+                tg_ldl_apply(n, W.Jq, W.Dd, sq, W.w, W.v);
+            } else tg_ldl_apply(n, W.Lm, W.Dd, sq, W.w, W.v);
             h1 = 0; h2 = 0;
             #pragma unroll 1
-            for (int i = lane; i < n; i += TG_NL) { h1 += W.s[i] * W.u[i]; h2 += W.s[i] * W.v[i]; }
+            for (int i = lane; i < n; i += TG_NL) { h1 += sq[i] * W.u[i]; h2 += sq[i] * W.v[i]; }
             tg_wsum2(h1, h2);
             h3 = 0.2 * h2;
             if (h1 < h3) {
@@ -996,12 +1274,17 @@ TG_QFN void tg_sqp_stage_qp(const TgLayout &L, const TgSqpWs &W)
                 #pragma unroll 1
                 // (scratch of the update: 5 n doubles; with L in J's storage they come from R's, free until the QP set-up)
                 for (int pass = 0; pass < 2; pass++) {
-                    if (lm_far) tg_ldl_update(n, pass == 0 ? 1 / h1 : -1 / h2, pass == 0 ? W.u : W.v, W.Jq, W.Dd, W.w, W.R);
-                    else tg_ldl_update(n, pass == 0 ? 1 / h1 : -1 / h2, pass == 0 ? W.u : W.v, W.Lm, W.Dd, W.w, W.Jq);
+                    if (lm_far) tg_ldl_update(n, pass == 0 ? 1 / h1 : -1 / h2, pass == 0 ? W.u : W.v, W.Jq, W.Dd, W.w, W.usc);
+                    else tg_ldl_update(n, pass == 0 ? 1 / h1 : -1 / h2, pass == 0 ? W.u : W.v, W.Lm, W.Dd, W.w, elim ? W.usc : W.Jq);
                 }
                 if (lm_far) {
-                    #pragma unroll 4
-                    for (int q = lane; q < n * n; q += TG_NL) W.Lm[q] = W.Jq[q];
+                    tg_copy_doubles(W.Lm, W.Jq, n * n, elim);
+                    TG_SYNC();
+                }
+                if (elim && W.nsfc) {
+                    // (the update's scratch reached into the rotation table)
+                    #pragma unroll 1
+                    for (int q = lane; q < (W.sfc_npts >> 2) * W.cpd * W.cpd; q += TG_NL) W.rotq[q] = W.rot[q];
                     TG_SYNC();
                 }
             }
@@ -1031,6 +1314,7 @@ TG_QFN void tg_sqp_stage_qp(const TgLayout &L, const TgSqpWs &W)
                 for (int i = lane; i < n1; i += TG_NL) W.Dd[i] = 1;
                 TG_SYNC();
                 ctl.need_reset = 0;
+                ident = true;
             }
             // ---- major iteration
             ctl.iter++;
@@ -1069,8 +1353,11 @@ TG_QFN void tg_sqp_stage_qp(const TgLayout &L, const TgSqpWs &W)
                 // (one call site per number of variables: the solver is inlined.  Only its first loop, which packs L next
                 // to J, reads Lsrc)
                 const double *Lsrc = (lm_far && lcopy) ? W.Jq : W.Lm;
-                if (SPLIT_NQ && nq == n) mode = tg_qp_solve(W, Lsrc, n, meq, rho, fl, ctl.nract, dfloor);
-                else mode = tg_qp_solve(W, Lsrc, nq, meq, rho, fl, ctl.nract, dfloor);
+                if (elim) {
+                    if (SPLIT_NQ && nq == n) mode = tg_qp_solve<true>(W, Lsrc, W.nf, meq, rho, fl, ctl.nract, dfloor, ident);
+                    else mode = tg_qp_solve<true>(W, Lsrc, nq == n ? W.nf : W.nf + 1, meq, rho, fl, ctl.nract, dfloor, ident);
+                } else if (SPLIT_NQ && nq == n) mode = tg_qp_solve<false>(W, Lsrc, n, meq, rho, fl, ctl.nract, dfloor, ident);
+                else mode = tg_qp_solve<false>(W, Lsrc, nq, meq, rho, fl, ctl.nract, dfloor, ident);
                 lcopy = false;        // the copy shared J's storage: the solve has overwritten it
                 if (attempt == 0 && mode == 6 && n == meq) mode = 4;
                 if (mode == TG_QP_OK) break;
@@ -1086,13 +1373,26 @@ TG_QFN void tg_sqp_stage_qp(const TgLayout &L, const TgSqpWs &W)
             if (mode != TG_QP_OK) { ctl.status = mode; ctl.state = TG_ST_DONE; break; }
             if (ctl.badlin) ctl.h4 = 1 - W.xq[n];
             // ---- gradient of the Lagrangian at the old point, merit weights
+            if (elim) {
+                #pragma unroll 1
+                for (int k = lane; k < ctl.nract; k += TG_NL) { const int j = W.ract[k]; W.act[k] = j; W.uq[k] = W.r[j]; }
+                TG_SYNC();
+            }
             #pragma unroll 1
             for (int i = lane; i < n; i += TG_NL) {
                 double h = W.g[i];
-                #pragma unroll 2
-                for (int k = 0; k < ctl.nract; k++) {
-                    const int j = W.ract[k];
-                    h -= (tg_is_sfc_row(W, j) ? tg_sfc_entry(W, W.rotq, j, i) : W.A[i * W.lda + tg_arow(W, j)]) * W.r[j];
+                if (elim) {
+                    #pragma unroll 4
+                    for (int k = 0; k < ctl.nract; k++) {
+                        const int j = W.act[k];
+                        h -= (tg_is_sfc_row(W, j) ? tg_sfc_entry(W, W.rotq, j, i) : W.A[i * W.lda + tg_arow(W, j)]) * W.uq[k];
+                    }
+                } else {
+                    #pragma unroll 2
+                    for (int k = 0; k < ctl.nract; k++) {
+                        const int j = W.ract[k];
+                        h -= (tg_is_sfc_row(W, j) ? tg_sfc_entry(W, W.rotq, j, i) : W.A[i * W.lda + tg_arow(W, j)]) * W.r[j];
+                    }
                 }
                 W.gl[i] = h;
                 W.s[i] = W.xq[i];
@@ -1153,7 +1453,11 @@ TG_FN void tg_sqp_solve(const TgLayout &L, const int *sp, const double *par, dou
         const int st = W.ctl->state;
         if (st == TG_ST_DONE) break;
         if (st == TG_ST_INIT || st == TG_ST_LS) { tg_sqp_stage_ls<D>(L, sp, par, W, trace, trace_cap); tg_sqp_stage_der<D>(L, sp, par, W); }
+#ifdef TG_FUSED_LM_FAR          // host tests of the lock-step kernels' variant of the stage (L worked on in J's storage)
+        else tg_sqp_stage_qp<true>(L, W);
+#else
         else tg_sqp_stage_qp<false>(L, W);
+#endif
     }
     #pragma unroll 1
     for (int i = TG_LANE(); i < L.n; i += TG_NL) xio[i] = W.x[i];
