@@ -59,12 +59,14 @@ struct TgSqpWs {
     // scratch
     double *u, *v, *w, *cf, *Jq, *R, *rsub, *z, *dq, *rq, *np, *uq, *xq, *hw, *rdi, *scratch;
     double *rotq;        // scratch: copy of rot for the violation scans of the QP stage
-    int *act, *iact;
+    int *act;
+    unsigned char *iact; // scratch: constraint (row or bound) is in the active set
     int *ract;           // persistent: active rows of the last QP, in the order they were added
     int *perm;           // scratch: QP order (free variables first, pinned ones behind them) -> index of the variable in x
     double *sq;          // scratch (pinned variables only): the step in QP order, for the factor update
     double *usc;         // scratch of the factor update (5 n doubles) while the copy of L occupies J's storage
     int jsz;             // doubles of J's storage
+    double *Ad;          // scratch (pinned variables only, else 0): copy of the dense inequality rows of A, row r at Ad + r n1
 };
 
 TG_HD int tg_odd(int v) { return v | 1; }
@@ -93,6 +95,11 @@ TG_HD int tg_rp(int j) { return j * (j + 1) / 2; }      // offset of column j of
 #define TG_PRAGMA_(x) _Pragma(#x)
 #define TG_PRAGMA(x) TG_PRAGMA_(x)
 #define TG_UNROLL_INNER TG_PRAGMA(unroll TG_UNROLL_N)
+// loops over the m constraint values (c, mu: global memory when the kernel does not stage the state).  Unrolled by 4 --
+// several loads in flight -- they cost C4's QP stage 2 %: its warps wait on instruction fetch before anything else.
+#ifndef TG_VIOL_UNROLL
+#define TG_VIOL_UNROLL 1
+#endif
 
 // The QP-stage functions are inlined into the lock-step QP kernel (one call site each; with the workspace carved
 // from the kernel's shared array the compiler then knows the address space of every access).  The fused kernel's
@@ -161,8 +168,13 @@ TG_HD void tg_sqp_carve4(const TgLayout &L, double *prefix, double *pbase, doubl
     TG_TAKE(rdi, n1);
     TG_TAKE(rotq, rotsz);
     if (w.ne && uscsz < 5 * n) o += (size_t)(5 * n - uscsz);
-    double *ints = base + o; o += (size_t)((n1 + 1 + w.nc + 1 + (w.ne ? n1 : 0)) / 2 + 1);
-    w.act = (int *)ints; w.iact = w.act + n1 + 1; w.perm = w.iact + w.nc + 1;
+    double *ints = base + o; o += (size_t)((n1 + 1 + (w.ne ? n1 : 0)) / 2 + 1);
+    w.act = (int *)ints; w.perm = w.act + n1 + 1;
+    w.iact = (unsigned char *)(base + o); o += (size_t)((w.nc + 1 + 7) / 8);
+    // (shapes with pinned variables run with their state in global memory -- C4 -- and scan the dense inequality rows
+    // in every iteration of the QP: a copy next to the scratch)
+    const int nd = m - 2 * L.n_sfc - L.meq;
+    if (w.ne && nd > 0) { TG_TAKE(Ad, nd * n1); } else w.Ad = 0;
     o += o & 1;
     if (nsq_) *nsq_ = o;
     if (ebase) { base = ebase - o; }
@@ -647,11 +659,14 @@ TG_QFN int tg_qp_solve(const TgSqpWs &W, const double *Lsrc, int nq, int meq, do
     bool pins = false;                          // ELIM: some pinned variable still has to move
     double dslack = rho * rho;                  // ELIM, augmented problem while pins move: the slack's entry of D
     if (ELIM) {
+        // A pin that is off by rounding alone (|c| <= 16 ulp of the variable: what x + (b - x) leaves behind) is put
+        // right by the step like any other, but its products with B and its multiplier -- 1e-16 relative to the
+        // gradient and to the merit function -- are not formed.
         #pragma unroll 1
         for (int e = lane; e < W.ne; e += TG_NL) {
             const double cv = W.c[tg_pin_row(W, e)];
             W.w[e] = cv;
-            if (cv != 0) pins = true;
+            if (fabs(cv) > 16 * 2.220446049250313e-16 * fabs(W.x[W.perm[W.nf + e]])) pins = true;
         }
         pins = tg_any(pins);
     }
@@ -766,6 +781,11 @@ TG_QFN int tg_qp_solve(const TgSqpWs &W, const double *Lsrc, int nq, int meq, do
     }
     #pragma unroll 1
     for (int p = lane; p < nc; p += TG_NL) { W.iact[p] = 0; W.r[p] = 0; }
+    const int nd = W.m - 2 * W.nsfc - meq;      // dense inequality rows
+    if (ELIM && nd > 0) {
+        #pragma unroll 4
+        for (int q = lane; q < nd * nx; q += TG_NL) { const int r = q / nx, i = q - r * nx; W.Ad[r * W.n1 + i] = W.A[i * W.lda + meq + r]; }
+    }
     TG_SYNC();
     // ---- unconstrained minimiser xq = -J J' g
     #pragma unroll 1
@@ -865,8 +885,14 @@ TG_QFN int tg_qp_solve(const TgSqpWs &W, const double *Lsrc, int nq, int meq, do
                 if (p < m) {
                     const int pa = t;          // row of A: the corridor rows are not stored
                     double h = 0, sc = fabs(W.c[p]);
-                    #pragma unroll 12
-                    for (int i = 0; i < nx; i++) { const double t = W.A[i * W.lda + pa] * W.xq[i]; h += t; sc += fabs(t); }
+                    if (ELIM && nd > 0) {
+                        const double *ar = W.Ad + (pa - meq) * W.n1;
+                        #pragma unroll 8
+                        for (int i = 0; i < nx; i++) { const double t = ar[i] * W.xq[i]; h += t; sc += fabs(t); }
+                    } else {
+                        #pragma unroll 8
+                        for (int i = 0; i < nx; i++) { const double t = W.A[i * W.lda + pa] * W.xq[i]; h += t; sc += fabs(t); }
+                    }
                     sv = h + W.c[p];
                     tol = 1e-13 * sc;
                 } else {
@@ -970,7 +996,7 @@ TG_QFN int tg_qp_solve(const TgSqpWs &W, const double *Lsrc, int nq, int meq, do
 TG_HD double tg_violation(const TgSqpWs &W, int meq, const double *weights)
 {
     double h = 0;
-    #pragma unroll 1
+    TG_PRAGMA(unroll TG_VIOL_UNROLL)
     for (int j = TG_LANE(); j < W.m; j += TG_NL) {
         const double cj = W.c[j];
         const double viol = j < meq ? fmax(-cj, cj) : fmax(-cj, 0.0);
@@ -1406,7 +1432,7 @@ TG_QFN void tg_sqp_stage_qp(const TgLayout &L, const TgSqpWs &W)
             for (int i = lane; i < n; i += TG_NL) gs += W.g[i] * W.s[i];
             gs = tg_wsum(gs);
             h1 = 0; h2 = 0;
-            #pragma unroll 1
+            TG_PRAGMA(unroll TG_VIOL_UNROLL)
             for (int j = lane; j < m; j += TG_NL) {
                 const double cj = W.c[j];
                 h2 += fmax(-cj, j < meq ? cj : 0.0);
