@@ -30,7 +30,7 @@ for item in sys.argv[3:]:
     x = x0.clone(); tgb.solve(bt.spec, par, x, jacobian=mode, buffers=bufs); torch.cuda.synchronize()
     lib.tg_set_stage_timing(0)
     st = (ctypes.c_double * 6)(); lib.tg_last_solve_stats(st, 6)
-    print("%-28s %s B=%d: %.1f ms (min %.1f) ls+der %.1f qp %.1f | status0 %.4f nit %.2f xsum %.10e -> %.0f traj/s" % (
-        item, mode, B, np.mean(ts), np.min(ts), st[0], st[1], (out["status"] == 0).float().mean().item(),
+    print("%-28s %s B=%d: %.1f ms (min %.1f) ls+der %.1f qp %.1f (%.3g flop) | status0 %.4f nit %.2f xsum %.10e -> %.0f traj/s" % (
+        item, mode, B, np.mean(ts), np.min(ts), st[0], st[1], st[2], (out["status"] == 0).float().mean().item(),
         out["nit"].float().mean().item(), out["x"].double().sum().item(), B / np.min(ts) * 1e3), flush=True)
     for k in sets: os.environ.pop(k, None)

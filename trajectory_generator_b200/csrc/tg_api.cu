@@ -209,16 +209,20 @@ static int tg_plan_solve(const TgShape &S, int B, TgSolvePlan *P)
     }
     if (P->smem_ls > budget) return tg_fail(3, "problem shape too large for the line-search kernel's shared memory");
     P->gs_ls = gs;
-    // QP: one warp per problem; two warps (64 lanes) when there are more than 32 variables, so that every
-    // lane-strided loop takes one pass.  Persistent state staged through shared memory when 16 problems still fit.
+    // QP: lanes per problem from the variables of the subproblem after the elimination of the terminal location rows
+    // (tg_sqp_qp_dim): 16, one warp, or two warps (64 lanes) beyond 32, so that every lane-strided loop takes one pass.  Persistent state staged through shared memory when 16 problems still fit.
     {
         const char *v = getenv("TG_QP_GS");
-        gs = v ? atoi(v) : (tg_sqp_qp_dim(S.L) > 32 ? 64 : 32);
+        // (16 lanes run with the state in global memory: only shapes with few dense inequality rows, whose copy sits next
+        // to the scratch -- C5: 239 ms against 276 ms with 32 lanes; C2, 11 such rows: 184 ms against 176 ms)
+        const int nd = S.L.m - 2 * S.L.n_sfc - S.L.meq;
+        gs = v ? atoi(v) : (tg_sqp_qp_dim(S.L) > 32 ? 64 : (tg_sqp_qp_dim(S.L) > 16 || nd > 4) ? 32 : 16);
         if (!(gs == 8 || gs == 16 || gs == 32 || gs == 64)) gs = 32;
     }
     P->gs_qp = gs;
     const size_t with_state = gs == 64 ? tg_qp_smem_g64(S, 1) : TG_DISPATCH(gs, tg_qp_smem_g8(S, 1), tg_qp_smem_g16(S, 1), tg_qp_smem_g32(S, 1));
     const size_t without = gs == 64 ? tg_qp_smem_g64(S, 0) : TG_DISPATCH(gs, tg_qp_smem_g8(S, 0), tg_qp_smem_g16(S, 0), tg_qp_smem_g32(S, 0));
+    // (16-lane groups: 8 problems per CTA, never staged by this rule -- measured: C5 239 ms unstaged, 260 ms staged)
     P->staged = with_state * 4 <= sm_total - 4096;
     if (const char *v = getenv("TG_QP_STAGED")) P->staged = atoi(v) != 0 && with_state <= budget;      // tuning override
     P->smem_qp = P->staged ? with_state : without;

@@ -7,4 +7,6 @@
 #define TG_SFX _g16
 // fixed shapes (tg_shape.h) with instantiations in this translation unit: the BASELINE configurations this group size serves
 #define TG_LS_FIXED TG_FIXED_CASE(TG_FIX_C3) TG_FIXED_CASE(TG_FIX_C4)
+// QP stage: the shapes whose subproblem has at most 16 variables once the terminal location rows are eliminated (tg_sqp_qp_dim)
+#define TG_QP_FIXED TG_FIXED_CASE(TG_FIX_C5A) TG_FIXED_CASE(TG_FIX_C5C)
 #include "tg_kernels_solve.inc"

@@ -9,5 +9,5 @@
 // shared memory (C2 / C5: QP stage -4 ... -8 %; the 64-lane kernels of tg_solve_g64.cu lose 5 % at 96 registers and keep 4)
 #define TG_QP_MIN_CTAS 5
 // fixed shapes (tg_shape.h) with instantiations in this translation unit: the BASELINE configurations this group size serves
-#define TG_QP_FIXED TG_FIXED_CASE(TG_FIX_C2) TG_FIXED_CASE(TG_FIX_C4) TG_FIXED_CASE(TG_FIX_C5A) TG_FIXED_CASE(TG_FIX_C5C)
+#define TG_QP_FIXED TG_FIXED_CASE(TG_FIX_C2) TG_FIXED_CASE(TG_FIX_C4)
 #include "tg_kernels_solve.inc"

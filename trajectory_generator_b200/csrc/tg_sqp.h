@@ -51,7 +51,7 @@ struct TgSqpWs {
     // variables pinned by an equality row with a single entry (zero-velocity terminal waypoints pin three control
     // points per coordinate, CF/waypoint_constraints.py:122-147): eliminated from the QP subproblem, see tg_qp_solve.
     // ne of them (nf = n - ne stay); esk / eek: pins at the start / at the end; erow_s / erow_e: first pin row of each
-    int ne, nf, esk, eek, erow_s, erow_e;
+    int ne, nf, esk, eek, rsk, rek, erow_s, erow_e;      // rsk / rek: rotated location triple at the start / at the end
     TgSqpCtl *ctl;
     // persistent
     double *x, *xl, *xu, *g, *s, *x0, *gl, *c, *mu, *r, *Lm, *Dd, *A;
@@ -62,7 +62,8 @@ struct TgSqpWs {
     int *act;
     unsigned char *iact; // scratch: constraint (row or bound) is in the active set
     int *ract;           // persistent: active rows of the last QP, in the order they were added
-    int *perm;           // scratch: QP order (free variables first, pinned ones behind them) -> index of the variable in x
+    int *perm;           // scratch: QP order (free coordinates first, eliminated ones behind them) -> index in rotated space
+    int *qix;            // scratch: the inverse (tg_qp_index of every index)
     double *sq;          // scratch (pinned variables only): the step in QP order, for the factor update
     double *usc;         // scratch of the factor update (5 n doubles) while the copy of L occupies J's storage
     int jsz;             // doubles of J's storage
@@ -77,9 +78,17 @@ TG_HD int tg_sqp_pinned(const TgLayout &L)
 #ifdef TG_NO_ELIM
     return 0;
 #else
-    const int sk = L.n_start == 3 * L.d, ek = L.n_end == 3 * L.d;
     if (L.d < 1 || L.N < 6) return 0;
-    return 3 * L.d * (sk + ek);
+    // 3 d per zero-velocity terminal waypoint (pins), d per plain location block (not the target form of the end
+    // waypoint, whose rows carry the scale factor too: TG_SP_END_KIND == 2 has its velocity in the parameter row)
+    // (other problem kinds that run the same stages -- the spline order converter -- have no such blocks: n_start = 0)
+    int s = L.n_start == 3 * L.d ? 3 : L.n_start == L.d ? 1 : 0;
+    int e = L.n_end == 3 * L.d ? 3 : (L.n_end == L.d && L.p_sdir == L.p_target_vel) ? 1 : 0;
+    // A shape with pins keeps its plain location rows: the rotation costs every step of the subproblem a pass over the
+    // step (rotated space <-> order of x), which the d rows less do not repay once the pins have shrunk the subproblem
+    // (measured on C4: QP stage 133 ms with the pins alone, 147 ms with the start triples rotated as well).
+    if (s == 3 || e == 3) { s = s == 3 ? 3 : 0; e = e == 3 ? 3 : 0; }
+    return L.d * (s + e);
 #endif
 }
 // variables of the (augmented) QP subproblem after the elimination: what the lanes of a group stride over
@@ -95,6 +104,9 @@ TG_HD int tg_rp(int j) { return j * (j + 1) / 2; }      // offset of column j of
 #define TG_PRAGMA_(x) _Pragma(#x)
 #define TG_PRAGMA(x) TG_PRAGMA_(x)
 #define TG_UNROLL_INNER TG_PRAGMA(unroll TG_UNROLL_N)
+// lanes of the shuffle-based recurrences (a warp, or the 16 lanes of a group) and their mask
+#define TG_SW (TG_GS >= 32 ? 32 : TG_GS)
+#define TG_SMASK() (TG_GS >= 32 ? 0xffffffffu : TG_GMASK())
 // loops over the m constraint values (c, mu: global memory when the kernel does not stage the state).  Unrolled by 4 --
 // several loads in flight -- they cost C4's QP stage 2 %: its warps wait on instruction fetch before anything else.
 #ifndef TG_VIOL_UNROLL
@@ -126,6 +138,8 @@ TG_HD void tg_sqp_carve4(const TgLayout &L, double *prefix, double *pbase, doubl
     w.sfc0 = L.r_sfcl; w.nsfc = L.n_sfc; w.sfc_npts = 4 * L.nint; w.cpN = L.N; w.cpd = L.d;
     w.ne = tg_sqp_pinned(L); w.nf = n - w.ne;
     w.esk = w.ne && L.n_start == 3 * L.d; w.eek = w.ne && L.n_end == 3 * L.d; w.erow_s = L.r_start; w.erow_e = L.r_end;
+    w.rsk = w.ne && !w.esk && !w.eek && L.n_start == L.d;
+    w.rek = w.ne && !w.esk && !w.eek && L.n_end == L.d && L.p_sdir == L.p_target_vel;
     const int nqm = w.nf + 1;            // largest QP subproblem (augmented)
     if (w.ne) w.ldq = tg_odd(nqm);
     size_t o = 0;
@@ -168,13 +182,14 @@ TG_HD void tg_sqp_carve4(const TgLayout &L, double *prefix, double *pbase, doubl
     TG_TAKE(rdi, n1);
     TG_TAKE(rotq, rotsz);
     if (w.ne && uscsz < 5 * n) o += (size_t)(5 * n - uscsz);
-    double *ints = base + o; o += (size_t)((n1 + 1 + (w.ne ? n1 : 0)) / 2 + 1);
-    w.act = (int *)ints; w.perm = w.act + n1 + 1;
+    double *ints = base + o; o += (size_t)((n1 + 1 + (w.ne ? 2 * n1 : 0)) / 2 + 1);
+    w.act = (int *)ints; w.perm = w.act + n1 + 1; w.qix = w.perm + n1;
     w.iact = (unsigned char *)(base + o); o += (size_t)((w.nc + 1 + 7) / 8);
     // (shapes with pinned variables run with their state in global memory -- C4 -- and scan the dense inequality rows
     // in every iteration of the QP: a copy next to the scratch)
+    // (a few rows only: shapes with many dense rows are small ones, whose state the kernel stages anyway)
     const int nd = m - 2 * L.n_sfc - L.meq;
-    if (w.ne && nd > 0) { TG_TAKE(Ad, nd * n1); } else w.Ad = 0;
+    if (w.ne && nd > 0 && nd <= 4) { TG_TAKE(Ad, nd * n1); } else w.Ad = 0;
     o += o & 1;
     if (nsq_) *nsq_ = o;
     if (ebase) { base = ebase - o; }
@@ -244,32 +259,76 @@ TG_HD double tg_sfc_entry(const TgSqpWs &W, const double *rot, int p, int i)
 }
 
 // ---------------------------------------------------------------------------
-// Pinned variables.  A zero-velocity terminal waypoint pins three control points per coordinate with rows that have a
-// single entry 1 (tg_jac_location, kind 1).  The QP subproblem then fixes the step of such a variable, d_i = -c_i
-// (zero once the pin holds), so the subproblem is solved over the other nf variables only: with the pinned variables
-// LAST in the order the factor L D L' of B is kept in ("QP order"), the factor of the free block is the leading block
-// of L and D.  C4: 34 -> 25 variables, 9 of its 15 equality rows gone, one warp per problem instead of two.
+// Eliminated variables.  The terminal location rows are linear with constant coefficients, and the QP subproblem can
+// be solved without them (null-space method):
+//  * a zero-velocity terminal waypoint pins three control points per coordinate with rows that have a single entry 1
+//    (tg_jac_location, kind 1): the step of such a variable is fixed, d_i = -c_i (zero once the pin holds);
+//  * a plain location row reads [1/6 2/3 1/6] (P0, P1, P2) = b per coordinate (kind 0).  With H the 3 x 3 Householder
+//    reflection that sends that row to -|w| e0, the rotated coordinates y = H (P0, P1, P2) have y0 pinned the same
+//    way, d_y0 = -c / (-|w|), and y1, y2 free.
+// The subproblem is then solved over the other nf coordinates only.  "Rotated space": x with every such triple replaced
+// by H x_triple (H is symmetric and orthogonal: the same product maps back).  "QP order": the rotated coordinates, the
+// eliminated ones LAST; the factor L D L' of B is kept in that order, so the factor of the free block is the
+// leading block of L and D.  Same iterates in exact arithmetic.  C4: 34 -> 22 variables and 12 of its 15 equality
+// rows gone, one warp per problem instead of two; C2 / C5: 17 -> 13, 4 of 8 equality rows gone.
 // ---------------------------------------------------------------------------
+#define TG_LOC_SIGMA (-0.70710678118654752440)       // the location row in rotated space: TG_LOC_SIGMA e0
+TG_HD double tg_loc_h(int a, int b)
+{
+    // H = I - 2 v v' / v'v, v = w / |w| + e0, w = [1/6 2/3 1/6]
+    const double h00 = -0.23570226039551584147, h01 = -0.94280904158206336587, h11 = 0.28066095096048549785,
+                 h12 = -0.17983476225987862554, h22 = 0.95504130943503034362;
+    const int lo = a < b ? a : b, hi = a < b ? b : a;
+    return lo == 0 ? (hi == 1 ? h01 : h00) : lo == 1 ? (hi == 1 ? h11 : h12) : h22;
+}
+// eliminated coordinates per coordinate axis at the start / at the end
+TG_HD int tg_elim_s(const TgSqpWs &W) { return 3 * W.esk + W.rsk; }
+TG_HD int tg_elim_e(const TgSqpWs &W) { return 3 * W.eek + W.rek; }
 TG_HD bool tg_is_pin_row(const TgSqpWs &W, int p)
 {
-    return (W.esk && p >= W.erow_s && p < W.erow_s + 3 * W.cpd) || (W.eek && p >= W.erow_e && p < W.erow_e + 3 * W.cpd);
+    return ((W.esk | W.rsk) && p >= W.erow_s && p < W.erow_s + tg_elim_s(W) * W.cpd) ||
+           ((W.eek | W.rek) && p >= W.erow_e && p < W.erow_e + tg_elim_e(W) * W.cpd);
 }
-// variable of x -> position in QP order (free variables keep their order; pinned ones follow, ascending)
+// first variable of the rotated triple that holds variable i of x, -1 if it is not in one
+TG_HD int tg_rot_base(const TgSqpWs &W, int i)
+{
+    const int N = W.cpN;
+    if (!(W.rsk | W.rek) || i >= W.cpd * N) return -1;
+    const int c = i / N, j = i - c * N;
+    if (W.rsk && j < 3) return c * N;
+    if (W.rek && j >= N - 3) return c * N + N - 3;
+    return -1;
+}
+// entry i of a vector of x taken to rotated space
+TG_HD double tg_rot_get(const TgSqpWs &W, const double *vec, int i)
+{
+    const int b = tg_rot_base(W, i);
+    if (b < 0) return vec[i];
+    const int a = i - b;
+    return tg_loc_h(a, 0) * vec[b] + tg_loc_h(a, 1) * vec[b + 1] + tg_loc_h(a, 2) * vec[b + 2];
+}
+// coordinate i of rotated space (same index as the variable of x it replaces) -> position in QP order (free
+// coordinates keep their order; eliminated ones follow, ascending)
 TG_HD int tg_qp_index(const TgSqpWs &W, int i)
 {
     if (!W.ne) return i;
-    const int N = W.cpN, per = 3 * (W.esk + W.eek);
+    const int N = W.cpN, es = tg_elim_s(W), ee = tg_elim_e(W), per = es + ee;
     if (i >= W.cpd * N) return i - W.cpd * per;
     const int c = i / N, j = i - c * N;
-    if (W.esk && j < 3) return W.nf + c * per + j;
-    if (W.eek && j >= N - 3) return W.nf + c * per + 3 * W.esk + (j - (N - 3));
-    return i - c * per - 3 * W.esk;
+    if (j < es) return W.nf + c * per + j;                                   // pins j = 0..2, or y0 of the rotated triple
+    if (ee && j >= N - 3 && j < N - 3 + ee) return W.nf + c * per + es + (j - (N - 3));
+    return i - c * per - es - (j >= N - 3 ? ee : 0);
 }
-// pinned variable e (QP position nf + e) -> its row
+// eliminated coordinate e (QP position nf + e) -> its row, and the row's entry there
 TG_HD int tg_pin_row(const TgSqpWs &W, int e)
 {
-    const int per = 3 * (W.esk + W.eek), c = e / per, t = e - c * per;
-    return (W.esk && t < 3) ? W.erow_s + 3 * c + t : W.erow_e + 3 * c + (t - 3 * W.esk);
+    const int es = tg_elim_s(W), per = es + tg_elim_e(W), c = e / per, t = e - c * per;
+    return t < es ? W.erow_s + es * c + t : W.erow_e + tg_elim_e(W) * c + (t - es);
+}
+TG_HD double tg_pin_sigma(const TgSqpWs &W, int e)
+{
+    const int es = tg_elim_s(W), per = es + tg_elim_e(W), t = e % per;
+    return (t < es ? W.rsk : W.rek) ? TG_LOC_SIGMA : 1.0;
 }
 
 // coefficient of the slack variable of the augmented problem in row j (SLSQP: -c for equalities, max(-c, 0) else)
@@ -306,10 +365,11 @@ TG_QFN void tg_ldl_update(int n, double sigma, double *z, double *Lm, double *Dd
     #pragma unroll 1
     for (int i = lane; i < n; i += TG_NL) vf[i] = z[i];
     TG_SYNC();
-#if defined(__CUDA_ARCH__) && TG_GS >= 32
-    // one warp, v in registers (entries lane and lane + 32), the pivot handed round with a shuffle (see the back
-    // substitution of tg_qp_directions); same operations in the same order.  n > 64: the shared-memory form.
-    if (n > 64) {
+#if defined(__CUDA_ARCH__) && TG_GS >= 16
+    // one warp (or half of one: 16-lane groups), v in registers (entries lane and lane + TG_SW), the pivot handed round
+    // with a shuffle (see the back substitution of tg_qp_directions); same operations in the same order.
+    // n > 2 TG_SW: the shared-memory form.
+    if (n > 2 * TG_SW) {
         if (TG_SERIAL_ACTIVE()) {
             #pragma unroll 1
             for (int i = 0; i < n - 1; i++) {
@@ -320,17 +380,17 @@ TG_QFN void tg_ldl_update(int n, double sigma, double *z, double *Lm, double *Dd
             }
         }
     } else if (TG_SERIAL_ACTIVE()) {
-        const int l32 = lane & 31;
-        double v0 = l32 < n ? vf[l32] : 0.0, v1 = l32 + 32 < n ? vf[l32 + 32] : 0.0;
+        const int l32 = lane & (TG_SW - 1);
+        double v0 = l32 < n ? vf[l32] : 0.0, v1 = l32 + TG_SW < n ? vf[l32 + TG_SW] : 0.0;
         #pragma unroll 2
         for (int i = 0; i < n - 1; i++) {
-            const double vv = __shfl_sync(0xffffffffu, i < 32 ? v0 : v1, i & 31);
+            const double vv = __shfl_sync(TG_SMASK(), i < TG_SW ? v0 : v1, i & (TG_SW - 1), TG_SW);
             const double *Li = Lm + i * n;
             if (l32 > i && l32 < n) v0 -= vv * Li[l32];
-            if (l32 + 32 > i && l32 + 32 < n) v1 -= vv * Li[l32 + 32];
+            if (l32 + TG_SW > i && l32 + TG_SW < n) v1 -= vv * Li[l32 + TG_SW];
         }
         if (l32 < n) vf[l32] = v0;
-        if (l32 + 32 < n) vf[l32 + 32] = v1;
+        if (l32 + TG_SW < n) vf[l32 + TG_SW] = v1;
     }
 #else
     if (TG_SERIAL_ACTIVE()) {
@@ -444,7 +504,17 @@ TG_HD double tg_normal_entry(const TgSqpWs &W, int meq, int p, int i)
     return i == i0 ? (q < W.n1 ? 1.0 : -1.0) : 0.0;
 }
 
-// ELIM: entry k of the QP's vectors belongs to variable perm[k] of x (k < nf) or to the slack (k == nf)
+// the same in rotated space (tg_rot_get of the normal)
+TG_HD double tg_normal_entry_r(const TgSqpWs &W, int meq, int p, int i)
+{
+    const int b = i < W.n ? tg_rot_base(W, i) : -1;
+    if (b < 0) return tg_normal_entry(W, meq, p, i);
+    const int a = i - b;
+    return tg_loc_h(a, 0) * tg_normal_entry(W, meq, p, b) + tg_loc_h(a, 1) * tg_normal_entry(W, meq, p, b + 1) +
+           tg_loc_h(a, 2) * tg_normal_entry(W, meq, p, b + 2);
+}
+
+// ELIM: entry k of the QP's vectors is coordinate perm[k] of rotated space (k < nf) or the slack (k == nf)
 #define TG_XI(k) (ELIM ? ((k) < W.nf ? W.perm[k] : W.n) : (k))
 
 template <bool ELIM>
@@ -452,12 +522,16 @@ TG_HD void tg_qp_normal(const TgSqpWs &W, int nq, int meq, int p, double *np, bo
 {
     const int lane = TG_LANE();
     if (ELIM) {
+        // the normal in the order of x first (W.hw: free until tg_qp_directions), one entry per lane; then rotated space
+        #pragma unroll 1
+        for (int i = lane; i <= W.n; i += TG_NL) W.hw[i] = (i < W.n || nq > W.nf) ? tg_normal_entry(W, meq, p, i) : 0.0;
+        TG_SYNC();
         #pragma unroll 1
         for (int k = lane; k < nq; k += TG_NL) {
-            double h = tg_normal_entry(W, meq, p, TG_XI(k));
-            if (coupled && k == W.nf)        // the slack moves the pinned variables along c_P (W.w)
+            double h = k < W.nf ? tg_rot_get(W, W.hw, W.perm[k]) : W.hw[W.n];
+            if (coupled && k == W.nf)        // the slack moves the eliminated coordinates along c_P / sigma (W.w)
                 #pragma unroll 1
-                for (int e = 0; e < W.ne; e++) h += tg_normal_entry(W, meq, p, W.perm[W.nf + e]) * W.w[e];
+                for (int e = 0; e < W.ne; e++) h += tg_rot_get(W, W.hw, W.perm[W.nf + e]) * W.w[e];
             np[k] = h;
         }
     } else if (p < W.m && tg_is_sfc_row(W, p)) {
@@ -477,28 +551,37 @@ TG_HD void tg_qp_normal(const TgSqpWs &W, int nq, int meq, int p, double *np, bo
     TG_SYNC();
 }
 
-// value of constraint p at xq (lane-parallel reduction; same result on all lanes).  W.np holds the normal of p
-// (tg_qp_normal): row p of A is not read a second time.  ELIM: xq stays in the order of x; `pins`: some pinned
-// variable has a non-zero step, whose product with the normal's entry is added
+// value of constraint p at the current point of the QP (lane-parallel reduction; same result on all lanes).  W.np holds
+// the normal of p (tg_qp_normal): row p of A is not read a second time.  ELIM: the point in QP coordinates is W.sq
+// (W.xq is its image in the order of x, for the scans); `pins`: some eliminated coordinate has a non-zero step -W.w
+// (the slack's share of it, in the augmented problem, is part of np[nf])
 template <bool ELIM>
-TG_HD double tg_qp_value(const TgSqpWs &W, int nq, int meq, int p, bool pins, bool coupled)
+TG_HD double tg_qp_value(const TgSqpWs &W, int nq, int meq, int p, bool pins)
 {
     if (p < W.m) {
         double s = 0;
         #pragma unroll 1
-        for (int i = TG_LANE(); i < nq; i += TG_NL) s += W.np[i] * W.xq[TG_XI(i)];
+        for (int i = TG_LANE(); i < nq; i += TG_NL) s += W.np[i] * (ELIM ? W.sq[i] : W.xq[i]);
         if (ELIM && pins) {
             #pragma unroll 1
-            for (int e = TG_LANE(); e < W.ne; e += TG_NL) {
-                const int i = W.perm[W.nf + e];
-                // (coupled: the slack's share of the pinned steps is part of np[nf]; what is left is -c_P)
-                s += tg_normal_entry(W, meq, p, i) * (coupled ? -W.w[e] : W.xq[i]);
-            }
+            for (int e = TG_LANE(); e < W.ne; e += TG_NL) s -= tg_normal_entry_r(W, meq, p, W.perm[W.nf + e]) * W.w[e];
         }
         return tg_wsum(s) + W.c[p];
     }
     const int q = p - W.m;
     return q < W.n1 ? W.xq[q] - W.u[q] : W.v[q - W.n1] - W.xq[q - W.n1];
+}
+
+// ELIM: a vector of QP coordinates y (free ones; the eliminated coordinate e has the value es W.w[e]) taken to the order
+// of x: entry i of the result.  rb: tg_rot_base(W, i).
+TG_HD double tg_qp_x_entry(const TgSqpWs &W, const double *y, double es, int i, int rb)
+{
+    if (rb < 0) { const int k = W.qix[i]; return k < W.nf ? y[k] : es * W.w[k - W.nf]; }
+    const int a = i - rb;
+    double h = 0;
+    #pragma unroll
+    for (int l = 0; l < 3; l++) { const int k = W.qix[rb + l]; h += tg_loc_h(a, l) * (k < W.nf ? y[k] : es * W.w[k - W.nf]); }
+    return h;
 }
 
 // d = J' np ; z = J2 d2 ; rq = R^-1 d1 ; returns |d2|^2 (= z.np) and |d|^2
@@ -532,11 +615,11 @@ TG_QFN void tg_qp_directions(const TgSqpWs &W, int nq, int iq, double &d2n, doub
         W.z[i] = h;
     }
     // back substitution R rq = d1 (column oriented; hw holds the running right-hand side, rdi = 1 / diag R)
-#if defined(__CUDA_ARCH__) && TG_GS >= 32
-    // One warp, the running right-hand side in registers (entries lane and lane + 32), the pivot handed round with
-    // a shuffle: no shared-memory round trip and no warp sync per step.  Same operations in the same order.
-    // (More than 64 active constraints -- shapes with more than 63 variables: the shared-memory form below.)
-    if (iq > 64) {
+#if defined(__CUDA_ARCH__) && TG_GS >= 16
+    // One warp (half of one: 16-lane groups), the running right-hand side in registers (entries lane and lane + TG_SW),
+    // the pivot handed round with a shuffle: no shared-memory round trip and no warp sync per step.  Same operations in
+    // the same order.  (More than 2 TG_SW active constraints: the shared-memory form below.)
+    if (iq > 2 * TG_SW) {
         if (TG_SERIAL_ACTIVE()) {
             #pragma unroll 1
             for (int j = iq - 1; j >= 0; j--) {
@@ -548,15 +631,15 @@ TG_QFN void tg_qp_directions(const TgSqpWs &W, int nq, int iq, double &d2n, doub
             }
         }
     } else if (TG_SERIAL_ACTIVE()) {
-        const int l32 = lane & 31;
-        double h0 = l32 < iq ? W.hw[l32] : 0.0, h1 = l32 + 32 < iq ? W.hw[l32 + 32] : 0.0;
+        const int l32 = lane & (TG_SW - 1);
+        double h0 = l32 < iq ? W.hw[l32] : 0.0, h1 = l32 + TG_SW < iq ? W.hw[l32 + TG_SW] : 0.0;
         #pragma unroll 2
         for (int j = iq - 1; j >= 0; j--) {
-            const double rj = __shfl_sync(0xffffffffu, j < 32 ? h0 : h1, j & 31) * W.rdi[j];
+            const double rj = __shfl_sync(TG_SMASK(), j < TG_SW ? h0 : h1, j & (TG_SW - 1), TG_SW) * W.rdi[j];
             const double *Rj = W.R + tg_rp(j);
-            if (l32 == (j & 31)) W.rq[j] = rj;
+            if (l32 == (j & (TG_SW - 1))) W.rq[j] = rj;
             if (l32 < j) h0 -= Rj[l32] * rj;
-            if (l32 + 32 < j) h1 -= Rj[l32 + 32] * rj;
+            if (l32 + TG_SW < j) h1 -= Rj[l32 + TG_SW] * rj;
         }
     }
 #else
@@ -664,9 +747,12 @@ TG_QFN int tg_qp_solve(const TgSqpWs &W, const double *Lsrc, int nq, int meq, do
         // gradient and to the merit function -- are not formed.
         #pragma unroll 1
         for (int e = lane; e < W.ne; e += TG_NL) {
-            const double cv = W.c[tg_pin_row(W, e)];
+            const double sg = tg_pin_sigma(W, e);
+            const double cv = W.c[tg_pin_row(W, e)] / sg;       // residual of the coordinate itself
+            const int i = W.perm[W.nf + e];
+            const double xs = sg == 1.0 ? fabs(W.x[i]) : fabs(W.x[i]) + fabs(W.x[i + 1]) + fabs(W.x[i + 2]);
             W.w[e] = cv;
-            if (fabs(cv) > 16 * 2.220446049250313e-16 * fabs(W.x[W.perm[W.nf + e]])) pins = true;
+            if (fabs(cv) > 16 * 2.220446049250313e-16 * xs) pins = true;
         }
         pins = tg_any(pins);
     }
@@ -722,9 +808,7 @@ TG_QFN int tg_qp_solve(const TgSqpWs &W, const double *Lsrc, int nq, int meq, do
     TG_SYNC();
     if (ELIM) {
         #pragma unroll 1
-        for (int e = lane; e < W.ne; e += TG_NL) W.xq[W.perm[W.nf + e]] = -W.w[e];
-        #pragma unroll 1
-        for (int k = lane; k < nq; k += TG_NL) W.rq[k] = W.g[TG_XI(k)];       // gradient in QP order
+        for (int k = lane; k < nq; k += TG_NL) W.rq[k] = k < W.nf ? tg_rot_get(W, W.g, W.perm[k]) : W.g[W.n];       // gradient in QP order
         TG_SYNC();
         if (pins) {
             // g_f + B_fP d_P = g_f + (B [0; d_P])_f
@@ -739,7 +823,7 @@ TG_QFN int tg_qp_solve(const TgSqpWs &W, const double *Lsrc, int nq, int meq, do
                 double gsl = 0, dd = 0;
                 #pragma unroll 1
                 for (int e = lane; e < W.ne; e += TG_NL) {
-                    gsl += W.w[e] * (W.g[W.perm[W.nf + e]] + W.sq[W.nf + e]);
+                    gsl += W.w[e] * (tg_rot_get(W, W.g, W.perm[W.nf + e]) + W.sq[W.nf + e]);
                     double h = W.w[e];
                     if (!ident)
                         #pragma unroll 1
@@ -782,7 +866,7 @@ TG_QFN int tg_qp_solve(const TgSqpWs &W, const double *Lsrc, int nq, int meq, do
     #pragma unroll 1
     for (int p = lane; p < nc; p += TG_NL) { W.iact[p] = 0; W.r[p] = 0; }
     const int nd = W.m - 2 * W.nsfc - meq;      // dense inequality rows
-    if (ELIM && nd > 0) {
+    if (ELIM && nd > 0 && nd <= 4) {
         #pragma unroll 4
         for (int q = lane; q < nd * nx; q += TG_NL) { const int r = q / nx, i = q - r * nx; W.Ad[r * W.n1 + i] = W.A[i * W.lda + meq + r]; }
     }
@@ -801,12 +885,15 @@ TG_QFN int tg_qp_solve(const TgSqpWs &W, const double *Lsrc, int nq, int meq, do
         double h = 0;
         TG_UNROLL_INNER
         for (int k = 0; k < nq; k++) h += W.Jq[k * ld + i] * W.dq[k];
-        W.xq[TG_XI(i)] = -h;
+        if (ELIM) W.sq[i] = -h; else W.xq[i] = -h;
     }
     TG_SYNC();
-    if (coupled) {
+    // ELIM: lane's entries of the step in the order of x (lane, lane + TG_NL, ...): rotated triple they belong to
+    if (ELIM) {
+        const double es = -(1 - (coupled ? W.sq[W.nf] : 0.0));
         #pragma unroll 1
-        for (int e = lane; e < W.ne; e += TG_NL) W.xq[W.perm[W.nf + e]] = -(1 - W.xq[W.n]) * W.w[e];
+        for (int i = lane; i < W.n; i += TG_NL) W.xq[i] = tg_qp_x_entry(W, W.sq, es, i, tg_rot_base(W, i));
+        if (nq > n && lane == 0) W.xq[W.n] = W.sq[W.nf];
         TG_SYNC();
     }
     int iq = 0;
@@ -885,7 +972,7 @@ TG_QFN int tg_qp_solve(const TgSqpWs &W, const double *Lsrc, int nq, int meq, do
                 if (p < m) {
                     const int pa = t;          // row of A: the corridor rows are not stored
                     double h = 0, sc = fabs(W.c[p]);
-                    if (ELIM && nd > 0) {
+                    if (ELIM && nd > 0 && nd <= 4) {
                         const double *ar = W.Ad + (pa - meq) * W.n1;
                         #pragma unroll 8
                         for (int i = 0; i < nx; i++) { const double t = ar[i] * W.xq[i]; h += t; sc += fabs(t); }
@@ -922,17 +1009,22 @@ TG_QFN int tg_qp_solve(const TgSqpWs &W, const double *Lsrc, int nq, int meq, do
                     // multipliers of the pin rows, from the pinned variables' entries of B d + g = sum of normals x multipliers
                     // (B d over all variables, QP order; W.Lm: the solve has overwritten the copy of L next to J)
                     #pragma unroll 1
-                    for (int k = lane; k < W.n; k += TG_NL) { W.hw[k] = W.xq[W.perm[k]]; if (ident) W.dq[k] = W.hw[k]; }
+                    const double ys = coupled ? W.sq[W.nf] : 0.0;
+                    #pragma unroll 1
+                    for (int k = lane; k < W.n; k += TG_NL) {
+                        W.hw[k] = k < W.nf ? W.sq[k] : -(1 - ys) * W.w[k - W.nf];
+                        if (ident) W.dq[k] = W.hw[k];
+                    }
                     TG_SYNC();
                     if (!ident) tg_ldl_apply(W.n, W.Lm, W.Dd, W.hw, W.z, W.dq);
                     #pragma unroll 1
                     for (int e = lane; e < W.ne; e += TG_NL) {
                         const int i = W.perm[W.nf + e];
-                        double h = W.dq[W.nf + e] + W.g[i];
+                        double h = W.dq[W.nf + e] + tg_rot_get(W, W.g, i);
                         #pragma unroll 1
                         for (int k = 0; k < iq; k++)
-                            if (W.act[k] < m) h -= tg_normal_entry(W, meq, W.act[k], i) * W.uq[k];
-                        W.r[tg_pin_row(W, e)] = h;
+                            if (W.act[k] < m) h -= tg_normal_entry_r(W, meq, W.act[k], i) * W.uq[k];
+                        W.r[tg_pin_row(W, e)] = h / tg_pin_sigma(W, e);
                     }
                     TG_SYNC();
                 }
@@ -941,7 +1033,7 @@ TG_QFN int tg_qp_solve(const TgSqpWs &W, const double *Lsrc, int nq, int meq, do
         }
         tg_qp_normal<ELIM>(W, nq, meq, ip, W.np, coupled);
         double uip = 0;
-        double sv = tg_qp_value<ELIM>(W, nq, meq, ip, pins, coupled);
+        double sv = tg_qp_value<ELIM>(W, nq, meq, ip, pins);
         #pragma unroll 1
         for (int inner = 0; inner < itmax; inner++) {
             tg_qp_directions(W, nq, iq, d2n, dn);
@@ -968,11 +1060,28 @@ TG_QFN int tg_qp_solve(const TgSqpWs &W, const double *Lsrc, int nq, int meq, do
             const bool primal = t2 < INFINITY;
             if (primal)
                 #pragma unroll 1
-                for (int i = lane; i < nq; i += TG_NL) W.xq[TG_XI(i)] += t * W.z[i];
-            if (primal && coupled)
+                for (int i = lane; i < nq; i += TG_NL) { if (ELIM) W.sq[i] += t * W.z[i]; else W.xq[i] += t * W.z[i]; }
+#ifdef TG_XQ_INCREMENTAL
+            if (ELIM && primal) {
+                // the same step in the order of x (eliminated coordinates move with the slack in the coupled problem)
+                const double es = coupled ? W.z[n] : 0.0;
                 #pragma unroll 1
-                for (int e = lane; e < W.ne; e += TG_NL) W.xq[W.perm[W.nf + e]] += t * W.z[n] * W.w[e];
+                for (int i = lane; i < W.n; i += TG_NL) W.xq[i] += t * tg_qp_x_entry(W, W.z, es, i, tg_rot_base(W, i));
+                if (nq > n && lane == 0) W.xq[W.n] += t * W.z[n];
+            }
             TG_SYNC();
+#else
+            TG_SYNC();
+            if (ELIM && primal) {
+                // the point in the order of x, for the scans (formed from the point itself, not step by step: the scans and
+                // tg_qp_value must see the same point to the last bits)
+                const double es = -(1 - (coupled ? W.sq[W.nf] : 0.0));
+                #pragma unroll 1
+                for (int i = lane; i < W.n; i += TG_NL) W.xq[i] = tg_qp_x_entry(W, W.sq, es, i, tg_rot_base(W, i));
+                if (nq > n && lane == 0) W.xq[W.n] = W.sq[W.nf];
+                TG_SYNC();
+            }
+#endif
             if (primal && t2 <= t1) {
                 if (lane == 0) { W.uq[iq] = uip; W.act[iq] = ip; W.iact[ip] = 1; }
                 TG_SYNC();
@@ -984,7 +1093,7 @@ TG_QFN int tg_qp_solve(const TgSqpWs &W, const double *Lsrc, int nq, int meq, do
             fl += 6.0 * (iq - 1 - l) * (nq + 0.5 * (iq - 1 - l));
             tg_qp_drop(W, nq, iq, l);
             if (primal) {
-                sv = tg_qp_value<ELIM>(W, nq, meq, ip, pins, coupled);
+                sv = tg_qp_value<ELIM>(W, nq, meq, ip, pins);
                 if (inner == itmax - 1) return 3;
             }
         }
@@ -1233,7 +1342,7 @@ TG_QFN void tg_sqp_stage_qp(const TgLayout &L, const TgSqpWs &W)
     }
     if (elim) {
         #pragma unroll 1
-        for (int i = lane; i < n; i += TG_NL) W.perm[tg_qp_index(W, i)] = i;
+        for (int i = lane; i < n; i += TG_NL) { const int k = tg_qp_index(W, i); W.perm[k] = i; W.qix[i] = k; }
         TG_SYNC();
     }
     if (ctl.state == TG_ST_UPDATE) {
@@ -1263,8 +1372,7 @@ TG_QFN void tg_sqp_stage_qp(const TgLayout &L, const TgSqpWs &W)
                         const int j = W.act[k];
                         h -= (tg_is_sfc_row(W, j) ? tg_sfc_entry(W, W.rotq, j, i) : W.A[i * W.lda + tg_arow(W, j)]) * W.uq[k];
                     }
-                    const int k = tg_qp_index(W, i);
-                    W.u[k] = h - W.gl[i]; W.sq[k] = W.s[i];
+                    W.v[i] = h - W.gl[i];           // (order of x; taken to QP order below)
                 } else {
                     #pragma unroll 2
                     for (int k = 0; k < ctl.nract; k++) {
@@ -1276,6 +1384,14 @@ TG_QFN void tg_sqp_stage_qp(const TgLayout &L, const TgSqpWs &W)
             }
             const double *sq = elim ? W.sq : W.s;         // the step in the order of the factor
             TG_SYNC();
+            if (elim) {
+                #pragma unroll 1
+                for (int i = lane; i < n; i += TG_NL) {
+                    const int k = tg_qp_index(W, i);
+                    W.u[k] = tg_rot_get(W, W.v, i); W.sq[k] = tg_rot_get(W, W.s, i);
+                }
+                TG_SYNC();
+            }
             if (lm_far) {
                 tg_copy_doubles(W.Jq, W.Lm, n * n, elim);
                 TG_SYNC();
