@@ -57,6 +57,17 @@ def load():
     return HostSim(OUT)
 
 
+def load_variant(tag, flags):
+    """A second host build with extra compiler flags (e.g. -DTG_NO_ELIM: the QP stage without the elimination of the
+    terminal location rows; -DTG_FUSED_LM_FAR: the lock-step kernels' variant of the stage)."""
+    out = os.path.join(HERE, "hostsim", "_build_hostsim_%s.so" % tag)
+    deps = [SRC] + [os.path.join(CSRC, f) for f in ("tg_eval.h", "tg_sqp.h", "tg_spec.h", "tg_smooth.h")]
+    if not os.path.exists(out) or any(os.path.getmtime(out) < os.path.getmtime(d) for d in deps):
+        subprocess.run(["g++", "-std=c++14", "-O2", "-fPIC", "-shared", "-ffp-contract=off", "-Wno-unknown-pragmas",
+                        "-DTG_WITH_SQP"] + list(flags) + ["-o", out, SRC], check=True, capture_output=True)
+    return HostSim(out)
+
+
 def scipy_core_solve(hs, pp, maxiter=100, acc=1e-6, record=None):
     """scipy's compiled SLSQP core (scipy.optimize._slsqplib.slsqp, the routine behind the reference's
     minimize(method='SLSQP') call) driven with the host-sim ANALYTIC evaluations, following the loop of
