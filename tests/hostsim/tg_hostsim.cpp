@@ -92,7 +92,7 @@ extern "C" void hs_fd_derivatives(const int *spec, const double *par, const doub
 extern "C" void hs_ldl_update(int n, double sigma, const double *z, double *Lm, double *Dd)
 {
     std::vector<double> zz(z, z + n), w(n + 1), sc(5 * (size_t)n + 5);
-    tg_ldl_update(n, sigma, zz.data(), Lm, Dd, w.data(), sc.data());
+    tg_ldl_update(n, sigma, zz.data(), Lm, Dd, w.data(), sc.data(), n);
 }
 #endif
 

@@ -41,6 +41,7 @@ struct TgSqpCtl {
     int state, iter, ireset, line, badlin, nfev, status, need_reset, maxiter, flags;
     int nract;           // rows (< m) with a non-zero multiplier after the last QP: W.ract[0 .. nract)
     int need_der;        // derivatives at the accepted point are still to be formed (stage DER)
+    int pins_hold;       // the eliminated coordinates have reached their values (tg_sqp_stage_qp): their block of B is frozen
 };
 enum { TG_ST_INIT = 0, TG_ST_QP, TG_ST_LS, TG_ST_UPDATE, TG_ST_DONE };
 #define TG_CTL_DOUBLES ((int)((sizeof(TgSqpCtl) + 7) / 8))
@@ -355,7 +356,8 @@ TG_HD double tg_slack_coeff(const TgSqpWs &W, int meq, int j) { return j < meq ?
 #else
 #define TG_MULADD2(a, b, c, d) ((a) * (b) + (c) * (d))
 #endif
-TG_QFN void tg_ldl_update(int n, double sigma, double *z, double *Lm, double *Dd, double *w, double *sc)
+// (ld: stride of the columns of Lm -- the update of the leading n x n block of a larger factor)
+TG_QFN void tg_ldl_update(int n, double sigma, double *z, double *Lm, double *Dd, double *w, double *sc, int ld)
 {
     const int lane = TG_LANE();
     if (sigma == 0) return;
@@ -375,7 +377,7 @@ TG_QFN void tg_ldl_update(int n, double sigma, double *z, double *Lm, double *Dd
             for (int i = 0; i < n - 1; i++) {
                 const double vv = vf[i];
                 #pragma unroll 1
-                for (int j = i + 1 + lane; j < n; j += TG_SERIAL_LANES) vf[j] -= vv * Lm[i * n + j];
+                for (int j = i + 1 + lane; j < n; j += TG_SERIAL_LANES) vf[j] -= vv * Lm[i * ld + j];
                 TG_SERIAL_SYNC();
             }
         }
@@ -385,7 +387,7 @@ TG_QFN void tg_ldl_update(int n, double sigma, double *z, double *Lm, double *Dd
         #pragma unroll 2
         for (int i = 0; i < n - 1; i++) {
             const double vv = __shfl_sync(TG_SMASK(), i < TG_SW ? v0 : v1, i & (TG_SW - 1), TG_SW);
-            const double *Li = Lm + i * n;
+            const double *Li = Lm + i * ld;
             if (l32 > i && l32 < n) v0 -= vv * Li[l32];
             if (l32 + TG_SW > i && l32 + TG_SW < n) v1 -= vv * Li[l32 + TG_SW];
         }
@@ -398,7 +400,7 @@ TG_QFN void tg_ldl_update(int n, double sigma, double *z, double *Lm, double *Dd
         for (int i = 0; i < n - 1; i++) {
             const double vv = vf[i];
             #pragma unroll 1
-            for (int j = i + 1 + lane; j < n; j += TG_SERIAL_LANES) vf[j] -= vv * Lm[i * n + j];
+            for (int j = i + 1 + lane; j < n; j += TG_SERIAL_LANES) vf[j] -= vv * Lm[i * ld + j];
             TG_SERIAL_SYNC();
         }
     }
@@ -447,13 +449,13 @@ TG_QFN void tg_ldl_update(int n, double sigma, double *z, double *Lm, double *Dd
         double zj = z[j];
         #pragma unroll 2
         for (int i = 0; i < j; i++) {
-            const double uu = Lm[i * n + j], vv = vf[i], beta = be[i];
+            const double uu = Lm[i * ld + j], vv = vf[i], beta = be[i];
             if (al[i] > 4) {
-                Lm[i * n + j] = TG_MULADD2(ga[i], uu, beta, zj);
+                Lm[i * ld + j] = TG_MULADD2(ga[i], uu, beta, zj);
                 zj -= vv * uu;
             } else {
                 zj -= vv * uu;
-                Lm[i * n + j] = uu + beta * zj;
+                Lm[i * ld + j] = uu + beta * zj;
             }
         }
     }
@@ -461,14 +463,14 @@ TG_QFN void tg_ldl_update(int n, double sigma, double *z, double *Lm, double *Dd
 }
 
 // out = L D L^T s  (tmp: n scratch)
-TG_QFN void tg_ldl_apply(int n, const double *Lm, const double *Dd, const double *s, double *tmp, double *out)
+TG_QFN void tg_ldl_apply(int n, const double *Lm, const double *Dd, const double *s, double *tmp, double *out, int ld)
 {
     const int lane = TG_LANE();
     #pragma unroll 1
     for (int i = lane; i < n; i += TG_NL) {
         double h = s[i];
         TG_UNROLL_INNER
-        for (int j = i + 1; j < n; j++) h += Lm[i * n + j] * s[j];
+        for (int j = i + 1; j < n; j++) h += Lm[i * ld + j] * s[j];
         tmp[i] = Dd[i] * h;
     }
     TG_SYNC();
@@ -476,7 +478,30 @@ TG_QFN void tg_ldl_apply(int n, const double *Lm, const double *Dd, const double
     for (int i = lane; i < n; i += TG_NL) {
         double h = tmp[i];
         TG_UNROLL_INNER
-        for (int j = 0; j < i; j++) h += Lm[j * n + i] * tmp[j];
+        for (int j = 0; j < i; j++) h += Lm[j * ld + i] * tmp[j];
+        out[i] = h;
+    }
+    TG_SYNC();
+}
+
+// entries i0 .. n-1 of L D L^T s with L in global memory (the multipliers of the eliminated coordinates at the end of
+// a subproblem): more loads in flight, and only the rows that are asked for in the second product
+TG_QFN void tg_ldl_apply_tail(int n, const double *Lm, const double *Dd, const double *s, double *tmp, double *out, int ld, int i0)
+{
+    const int lane = TG_LANE();
+    #pragma unroll 1
+    for (int i = lane; i < n; i += TG_NL) {
+        double h = s[i];
+        #pragma unroll 8
+        for (int j = i + 1; j < n; j++) h += Lm[i * ld + j] * s[j];
+        tmp[i] = Dd[i] * h;
+    }
+    TG_SYNC();
+    #pragma unroll 1
+    for (int i = i0 + lane; i < n; i += TG_NL) {
+        double h = tmp[i];
+        #pragma unroll 8
+        for (int j = 0; j < i; j++) h += Lm[j * ld + i] * tmp[j];
         out[i] = h;
     }
     TG_SYNC();
@@ -733,7 +758,7 @@ TG_QFN void tg_qp_drop(const TgSqpWs &W, int nq, int &iq, int l)
 // order of x.  Lsrc / W.Lm / W.Dd: the factor of B in QP order.
 template <bool ELIM>
 TG_QFN int tg_qp_solve(const TgSqpWs &W, const double *Lsrc, int nq, int meq, double rho, double &fl, int &nract, double dfloor,
-                       bool ident)
+                       bool ident, bool hold, bool &moving)
 {
     const int lane = TG_LANE(), ld = W.ldq, m = W.m;
     const int n = ELIM ? W.nf : W.n;            // variables of the plain subproblem
@@ -754,8 +779,9 @@ TG_QFN int tg_qp_solve(const TgSqpWs &W, const double *Lsrc, int nq, int meq, do
             W.w[e] = cv;
             if (fabs(cv) > 16 * 2.220446049250313e-16 * xs) pins = true;
         }
-        pins = tg_any(pins);
+        pins = tg_any(pins) && !hold;       // (hold: they have reached their values before; their block of B is frozen)
     }
+    moving = pins;
     const bool coupled = ELIM && pins && nq > n;      // the slack's column of J is not a unit vector
     if (ELIM && pins) {
         // W.sq = B [0; d_P], d_P = -c_P: what the pinned variables' fixed step adds to the gradient of the free ones
@@ -764,7 +790,7 @@ TG_QFN int tg_qp_solve(const TgSqpWs &W, const double *Lsrc, int nq, int meq, do
         #pragma unroll 1
         for (int k = lane; k < W.n; k += TG_NL) { W.hw[k] = k < W.nf ? 0.0 : -W.w[k - W.nf]; if (ident) W.sq[k] = W.hw[k]; }
         TG_SYNC();
-        if (!ident) tg_ldl_apply(W.n, Lsrc, W.Dd, W.hw, W.rdi, W.sq);
+        if (!ident) tg_ldl_apply(W.n, Lsrc, W.Dd, W.hw, W.rdi, W.sq, W.n);
     }
     const double EPS_DEP = 1e-26;     // |d2|^2 <= EPS_DEP |d|^2 : normal lies in the span of the active ones
     // ---- J = L^-T D^-1/2 (upper triangular), augmented entry 1/rho.  L is read n^2/2 times per lane: copy it next
@@ -1016,7 +1042,7 @@ TG_QFN int tg_qp_solve(const TgSqpWs &W, const double *Lsrc, int nq, int meq, do
                         if (ident) W.dq[k] = W.hw[k];
                     }
                     TG_SYNC();
-                    if (!ident) tg_ldl_apply(W.n, W.Lm, W.Dd, W.hw, W.z, W.dq);
+                    if (!ident) tg_ldl_apply_tail(W.n, W.Lm, W.Dd, W.hw, W.z, W.dq, W.n, W.nf);
                     #pragma unroll 1
                     for (int e = lane; e < W.ne; e += TG_NL) {
                         const int i = W.perm[W.nf + e];
@@ -1138,6 +1164,12 @@ TG_FN void tg_sqp_fd_derivatives(const TgLayout &L, const int *sp, const double 
     // the objective and the light blocks: one perturbed evaluation per variable
     #pragma unroll 1
     for (int i = 0; i < n; i++) {
+        // a pinned control point that has reached its value does not move any more and its column of the derivatives is
+        // not used any more (tg_sqp_stage_qp: its block of B is frozen): no evaluation for it
+        if (W.ne && W.ctl->pins_hold && i < W.cpd * W.cpN) {
+            const int j = i % W.cpN;
+            if ((W.esk && j < 3) || (W.eek && j >= W.cpN - 3)) continue;
+        }
         const double xi = W.x[i];
         const double h = tg_fd_step(xi, W.xl[i], W.xu[i]);
         TG_SYNC();
@@ -1187,7 +1219,7 @@ TG_FN void tg_sqp_begin(const TgLayout &L, const TgSqpWs &W, const double *xin, 
         TgSqpCtl c;
         c.f = 0; c.f0 = 0; c.t0 = 0; c.h3 = 0; c.h4 = 1; c.alpha = 1; c.acc = acc; c.flops = 0;
         c.state = TG_ST_INIT; c.iter = 0; c.ireset = 0; c.line = 0; c.badlin = 0; c.nfev = 0; c.status = -1;
-        c.need_reset = 1; c.maxiter = maxiter; c.flags = flags; c.nract = 0; c.need_der = 0;
+        c.need_reset = 1; c.maxiter = maxiter; c.flags = flags; c.nract = 0; c.need_der = 0; c.pins_hold = 0;
         *W.ctl = c;
     }
     TG_SYNC();
@@ -1392,22 +1424,26 @@ TG_QFN void tg_sqp_stage_qp(const TgLayout &L, const TgSqpWs &W)
                 }
                 TG_SYNC();
             }
+            // Once the eliminated coordinates have reached their values their steps are zero for good, and their rows
+            // and columns of B never enter a subproblem again: only the leading nf x nf block of the factor (QP order)
+            // is updated from then on -- the same free block in exact arithmetic.
+            const int nb = (elim && ctl.pins_hold) ? W.nf : n;
             if (lm_far) {
-                tg_copy_doubles(W.Jq, W.Lm, n * n, elim);
+                tg_copy_doubles(W.Jq, W.Lm, nb * n, elim);
                 TG_SYNC();
                 lcopy = true;
-                tg_ldl_apply(n, W.Jq, W.Dd, sq, W.w, W.v);
-            } else tg_ldl_apply(n, W.Lm, W.Dd, sq, W.w, W.v);
+                tg_ldl_apply(nb, W.Jq, W.Dd, sq, W.w, W.v, n);
+            } else tg_ldl_apply(nb, W.Lm, W.Dd, sq, W.w, W.v, n);
             h1 = 0; h2 = 0;
             #pragma unroll 1
-            for (int i = lane; i < n; i += TG_NL) { h1 += sq[i] * W.u[i]; h2 += sq[i] * W.v[i]; }
+            for (int i = lane; i < nb; i += TG_NL) { h1 += sq[i] * W.u[i]; h2 += sq[i] * W.v[i]; }
             tg_wsum2(h1, h2);
             h3 = 0.2 * h2;
             if (h1 < h3) {
                 const double h4 = (h2 - h3) / (h2 - h1);
                 h1 = h3;
                 #pragma unroll 1
-                for (int i = lane; i < n; i += TG_NL) W.u[i] = h4 * W.u[i] + (1 - h4) * W.v[i];
+                for (int i = lane; i < nb; i += TG_NL) W.u[i] = h4 * W.u[i] + (1 - h4) * W.v[i];
             }
             TG_SYNC();
             fl += 2.0 * n * ctl.nract + 6.0 * n * n + 8.0 * n;         // u = grad L - gl ; v = B s ; two rank-one updates of L D L'
@@ -1416,11 +1452,11 @@ TG_QFN void tg_sqp_stage_qp(const TgLayout &L, const TgSqpWs &W)
                 #pragma unroll 1
                 // (scratch of the update: 5 n doubles; with L in J's storage they come from R's, free until the QP set-up)
                 for (int pass = 0; pass < 2; pass++) {
-                    if (lm_far) tg_ldl_update(n, pass == 0 ? 1 / h1 : -1 / h2, pass == 0 ? W.u : W.v, W.Jq, W.Dd, W.w, W.usc);
-                    else tg_ldl_update(n, pass == 0 ? 1 / h1 : -1 / h2, pass == 0 ? W.u : W.v, W.Lm, W.Dd, W.w, elim ? W.usc : W.Jq);
+                    if (lm_far) tg_ldl_update(nb, pass == 0 ? 1 / h1 : -1 / h2, pass == 0 ? W.u : W.v, W.Jq, W.Dd, W.w, W.usc, n);
+                    else tg_ldl_update(nb, pass == 0 ? 1 / h1 : -1 / h2, pass == 0 ? W.u : W.v, W.Lm, W.Dd, W.w, elim ? W.usc : W.Jq, n);
                 }
                 if (lm_far) {
-                    tg_copy_doubles(W.Lm, W.Jq, n * n, elim);
+                    tg_copy_doubles(W.Lm, W.Jq, nb * n, elim);
                     TG_SYNC();
                 }
                 if (elim && W.nsfc) {
@@ -1474,6 +1510,7 @@ TG_QFN void tg_sqp_stage_qp(const TgLayout &L, const TgSqpWs &W)
             // problems iterating the way the reference does.
             int mode = 0, nq = n;
             double rho = 0, dfloor = 0;
+            bool moving = false;
             #pragma unroll 1
             for (int attempt = 0; attempt < 8; attempt++) {
                 if (attempt >= 1 && nq == n) {
@@ -1496,10 +1533,10 @@ TG_QFN void tg_sqp_stage_qp(const TgLayout &L, const TgSqpWs &W)
                 // to J, reads Lsrc)
                 const double *Lsrc = (lm_far && lcopy) ? W.Jq : W.Lm;
                 if (elim) {
-                    if (SPLIT_NQ && nq == n) mode = tg_qp_solve<true>(W, Lsrc, W.nf, meq, rho, fl, ctl.nract, dfloor, ident);
-                    else mode = tg_qp_solve<true>(W, Lsrc, nq == n ? W.nf : W.nf + 1, meq, rho, fl, ctl.nract, dfloor, ident);
-                } else if (SPLIT_NQ && nq == n) mode = tg_qp_solve<false>(W, Lsrc, n, meq, rho, fl, ctl.nract, dfloor, ident);
-                else mode = tg_qp_solve<false>(W, Lsrc, nq, meq, rho, fl, ctl.nract, dfloor, ident);
+                    if (SPLIT_NQ && nq == n) mode = tg_qp_solve<true>(W, Lsrc, W.nf, meq, rho, fl, ctl.nract, dfloor, ident, ctl.pins_hold != 0, moving);
+                    else mode = tg_qp_solve<true>(W, Lsrc, nq == n ? W.nf : W.nf + 1, meq, rho, fl, ctl.nract, dfloor, ident, ctl.pins_hold != 0, moving);
+                } else if (SPLIT_NQ && nq == n) mode = tg_qp_solve<false>(W, Lsrc, n, meq, rho, fl, ctl.nract, dfloor, ident, ctl.pins_hold != 0, moving);
+                else mode = tg_qp_solve<false>(W, Lsrc, nq, meq, rho, fl, ctl.nract, dfloor, ident, ctl.pins_hold != 0, moving);
                 lcopy = false;        // the copy shared J's storage: the solve has overwritten it
                 if (attempt == 0 && mode == 6 && n == meq) mode = 4;
                 if (mode == TG_QP_OK) break;
@@ -1509,10 +1546,13 @@ TG_QFN void tg_sqp_stage_qp(const TgLayout &L, const TgSqpWs &W)
             {
                 double dmin = 1e300, dmax = 0;
                 for (int i = 0; i < n; i++) { dmin = fmin(dmin, W.Dd[i]); dmax = fmax(dmax, W.Dd[i]); }
-                printf("iter %3d mode %d badlin %d rho %.0e  D in [%.2e, %.2e]  f %.8g\n", ctl.iter, mode, ctl.badlin, rho, dmin, dmax, ctl.f);
+                printf("iter %3d mode %d badlin %d rho %.0e  D in [%.2e, %.2e]  f %.8g hold %d moving %d\n", ctl.iter, mode, ctl.badlin, rho, dmin, dmax, ctl.f, ctl.pins_hold, (int)moving);
             }
 #endif
             if (mode != TG_QP_OK) { ctl.status = mode; ctl.state = TG_ST_DONE; break; }
+            // (shapes with pinned control points only: with rotated triples alone the saving is a few per cent of the
+            // factor update, and nothing in the derivative stage)
+            if (elim && (W.esk | W.eek) && !moving) ctl.pins_hold = 1;
             if (ctl.badlin) ctl.h4 = 1 - W.xq[n];
             // ---- gradient of the Lagrangian at the old point, merit weights
             if (elim) {
