@@ -69,10 +69,12 @@ def test_augmented_subproblem_while_the_pins_move(builds):
 
 
 def test_fixture_shapes_with_and_without_elimination(builds):
-    """every recorded solve fixture: same status and iteration count over the first 8 iterations' worth of work"""
+    """every fixture shape (pins at the start, target form of the end waypoint, both kinds of terminal block, ...): the
+    first iterates agree"""
     far, fused, full = builds
     ns = helpers.product_namespace()
-    for name in problems.SOLVE:
+    for name in problems.ALL:
         d, cc, kw = problems.ALL[name](ns)
         pp = pack_problem(d, cc, kw.get("objective_function_type", "minimal_velocity_and_time_path"), kw.get("num_intervals_free_space"))
-        _first_iterates_agree(far, full, pp, 5, 1e-9)
+        # (three iterations: features3d amplifies rounding by 1e3 ... 1e4 per iteration -- 2e-14, 3e-11, 3e-10, 5e-6)
+        _first_iterates_agree(far, full, pp, 3, 1e-9)
