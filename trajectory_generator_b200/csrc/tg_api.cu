@@ -201,7 +201,9 @@ static int tg_plan_solve(const TgShape &S, int B, TgSolvePlan *P)
     // ---- lock step
     P->np = tg_sqp_persistent_doubles(S.L);
     // line search: smallest group that leaves >= 8 resident warps' worth of shared memory per SM
-    int gs = tg_env_gs("TG_LS_GS", tg_default_gs(S.L));
+    // (shapes with more than 32 variables: 16 lanes at least -- C4 fits 8-lane groups since its derivative stage stages
+    // less, but runs 3 % slower with them)
+    int gs = tg_env_gs("TG_LS_GS", S.L.n > 32 && tg_default_gs(S.L) < 16 ? 16 : tg_default_gs(S.L));
     for (;;) {
         P->smem_ls = TG_DISPATCH(gs, tg_ls_smem_g8(S), tg_ls_smem_g16(S), tg_ls_smem_g32(S));
         if (P->smem_ls * 2 <= sm_total - 2048 || gs == 32) break;

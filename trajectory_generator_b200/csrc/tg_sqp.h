@@ -123,7 +123,7 @@ TG_HD int tg_rp(int j) { return j * (j + 1) / 2; }      // offset of column j of
 #define TG_QFN TG_FN
 #endif
 
-// Carves the per-problem state.  The persistent block is [ctl | x xl xu g s x0 | c mu | gl r Dd | ract rot | A | Lm]; its first
+// Carves the per-problem state.  The persistent block is [ctl | x xl xu g c | s x0 mu | gl r Dd | ract rot | A | Lm]; its first
 // `npre` doubles (everything the line-search stage touches except A) may be staged at `prefix` while the rest
 // stays at `pbase` (+ offset) -- pass prefix == pbase for one contiguous block.  The scratch block is
 // [QP-stage scratch | evaluation scratch (cf, evaluators' scratch)]; `ebase` != 0 places the evaluation scratch
@@ -147,8 +147,10 @@ TG_HD void tg_sqp_carve4(const TgLayout &L, double *prefix, double *pbase, doubl
     double *base = prefix;
 #define TG_TAKE(field, count) w.field = base + o; o += (size_t)(count)
     w.ctl = (TgSqpCtl *)base; o += TG_CTL_DOUBLES;
-    TG_TAKE(x, n1); TG_TAKE(xl, n1); TG_TAKE(xu, n1); TG_TAKE(g, n1); TG_TAKE(s, n1); TG_TAKE(x0, n1);
-    TG_TAKE(c, m + 1); TG_TAKE(mu, m + 1);
+    // (what the derivative stage touches first: its kernel stages [ctl .. c] only, tg_sqp_prefix_fd_doubles)
+    TG_TAKE(x, n1); TG_TAKE(xl, n1); TG_TAKE(xu, n1); TG_TAKE(g, n1); TG_TAKE(c, m + 1);
+    o += o & 1;
+    TG_TAKE(s, n1); TG_TAKE(x0, n1); TG_TAKE(mu, m + 1);
     o += o & 1;                  // even counts: the staged pieces are moved with 16-byte accesses (double2 / 16-byte cp.async)
     if (npre_) *npre_ = o;
     base = pbase;
@@ -194,7 +196,8 @@ TG_HD void tg_sqp_carve4(const TgLayout &L, double *prefix, double *pbase, doubl
     o += o & 1;
     if (nsq_) *nsq_ = o;
     if (ebase) { base = ebase - o; }
-    TG_TAKE(cf, m + 1); TG_TAKE(scratch, tg_scratch_doubles(L));       // <- all the line-search stage needs
+    // cf: constraint values at a perturbed point (finite-difference mode): the rows in front of the turning row only
+    TG_TAKE(cf, L.r_turn + 1); TG_TAKE(scratch, tg_scratch_doubles(L));       // <- all the line-search stage needs
 #undef TG_TAKE
     if (ns_) *ns_ = o;
     if (W) *W = w;
@@ -212,7 +215,13 @@ TG_HD void tg_sqp_carve2(const TgLayout &L, double *pbase, double *sbase, TgSqpW
 }
 
 // scratch needed by the line-search stage alone (cf + the evaluators' scratch) / by the QP stage alone
-TG_HD size_t tg_sqp_ls_scratch_doubles(const TgLayout &L) { return (size_t)L.m + 1 + tg_scratch_doubles(L); }
+TG_HD size_t tg_sqp_ls_scratch_doubles(const TgLayout &L) { return (size_t)L.r_turn + 1 + tg_scratch_doubles(L); }
+// front of the persistent block that the derivative stage touches: [ctl | x xl xu g | c], even
+TG_HD size_t tg_sqp_prefix_fd_doubles(const TgLayout &L)
+{
+    const size_t o = (size_t)TG_CTL_DOUBLES + 4 * (size_t)(L.n + 1) + (size_t)L.m + 1;
+    return o + (o & 1);
+}
 TG_HD size_t tg_sqp_qp_scratch_doubles(const TgLayout &L) { size_t a, b, c, d; tg_sqp_carve4(L, 0, 0, 0, 0, 0, &a, &b, &c, &d); return d; }
 TG_HD size_t tg_sqp_prefix_doubles(const TgLayout &L) { size_t a, b, c; tg_sqp_carve3(L, 0, 0, 0, 0, &a, &b, &c); return c; }
 
