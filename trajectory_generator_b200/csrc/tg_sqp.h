@@ -1342,11 +1342,12 @@ TG_HD void tg_copy_doubles(double *dst, const double *src, int count, bool wide)
 {
     const int lane = TG_LANE();
 #ifdef __CUDA_ARCH__
-    if (wide && (count & 1) == 0 && ((((size_t)dst) | ((size_t)src)) & 15) == 0) {
+    if (wide && ((((size_t)dst) | ((size_t)src)) & 15) == 0) {
         double2 *d2 = reinterpret_cast<double2 *>(dst);
         const double2 *s2 = reinterpret_cast<const double2 *>(src);
         #pragma unroll 8
         for (int q = lane; q < count / 2; q += TG_NL) d2[q] = s2[q];
+        if ((count & 1) && lane == 0) dst[count - 1] = src[count - 1];
         return;
     }
 #endif
