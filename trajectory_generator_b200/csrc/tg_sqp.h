@@ -96,9 +96,11 @@ TG_HD int tg_sqp_pinned(const TgLayout &L)
 TG_HD int tg_sqp_qp_dim(const TgLayout &L) { return L.n - tg_sqp_pinned(L) + 1; }
 TG_HD int tg_rp(int j) { return j * (j + 1) / 2; }      // offset of column j of the packed upper-triangular R
 
-// unroll factor of the sequential inner products / updates of the QP stage (trip counts are n <= 62)
+// unroll factor of the sequential inner products / updates of the QP stage (trip counts are n <= 62).  2 since the end
+// of round 2 (was 4): the stage waits on instruction fetch, and the smaller loops are worth 0.6 % (C4) ... 1.2 % (C3);
+// 1 loses 8 % on C3.
 #ifndef TG_UNROLL_N
-#define TG_UNROLL_N 4
+#define TG_UNROLL_N 2
 #endif
 // (Two interleaved accumulator chains per inner product -- even / odd terms, added at the end -- were measured in round 2:
 // QP stage +-0 % on C3 / C4, +3 ... 5 % on C2 / C5: the chains are not what the stage waits on once the loads are counted.)
