@@ -112,6 +112,26 @@ TG_HD int tg_rp(int j) { return j * (j + 1) / 2; }      // offset of column j of
 #define TG_SMASK() (TG_GS >= 32 ? 0xffffffffu : TG_GMASK())
 // loops over the m constraint values (c, mu: global memory when the kernel does not stage the state).  Unrolled by 4 --
 // several loads in flight -- they cost C4's QP stage 2 %: its warps wait on instruction fetch before anything else.
+// Unroll factors of a few more loops of the stage.  Its one-warp kernels wait on instruction fetch before anything else
+// (profiles/README.md), and unrolling these loops costs more in fetches than it saves in issue slots -- measured on C4,
+// 65,536 problems: products with the active rows behind the Lagrangian gradient 4 -> 1 and the scan of the copied dense
+// rows 8 -> 1: QP stage 126 -> 110 ms.
+// (the two-warp kernels do not wait on fetches -- C3 loses 2 % without the unrolling)
+#ifndef TG_LAG_UNROLL
+#define TG_LAG_UNROLL (TG_GS == 64 ? 4 : 1)
+#endif
+#ifndef TG_DENSE_UNROLL
+#define TG_DENSE_UNROLL (TG_GS == 64 ? 8 : 1)
+#endif
+#ifndef TG_REC_UNROLL
+#define TG_REC_UNROLL 2
+#endif
+#ifndef TG_DENSE_FAR_UNROLL
+#define TG_DENSE_FAR_UNROLL 8
+#endif
+#ifndef TG_LAG_FAR_UNROLL
+#define TG_LAG_FAR_UNROLL 2
+#endif
 #ifndef TG_VIOL_UNROLL
 #define TG_VIOL_UNROLL 1
 #endif
@@ -395,7 +415,7 @@ TG_QFN void tg_ldl_update(int n, double sigma, double *z, double *Lm, double *Dd
     } else if (TG_SERIAL_ACTIVE()) {
         const int l32 = lane & (TG_SW - 1);
         double v0 = l32 < n ? vf[l32] : 0.0, v1 = l32 + TG_SW < n ? vf[l32 + TG_SW] : 0.0;
-        #pragma unroll 2
+        TG_PRAGMA(unroll TG_REC_UNROLL)
         for (int i = 0; i < n - 1; i++) {
             const double vv = __shfl_sync(TG_SMASK(), i < TG_SW ? v0 : v1, i & (TG_SW - 1), TG_SW);
             const double *Li = Lm + i * ld;
@@ -458,7 +478,7 @@ TG_QFN void tg_ldl_update(int n, double sigma, double *z, double *Lm, double *Dd
     #pragma unroll 1
     for (int j = 1 + lane; j < n; j += TG_NL) {
         double zj = z[j];
-        #pragma unroll 2
+        TG_PRAGMA(unroll TG_REC_UNROLL)
         for (int i = 0; i < j; i++) {
             const double uu = Lm[i * ld + j], vv = vf[i], beta = be[i];
             if (al[i] > 4) {
@@ -669,7 +689,7 @@ TG_QFN void tg_qp_directions(const TgSqpWs &W, int nq, int iq, double &d2n, doub
     } else if (TG_SERIAL_ACTIVE()) {
         const int l32 = lane & (TG_SW - 1);
         double h0 = l32 < iq ? W.hw[l32] : 0.0, h1 = l32 + TG_SW < iq ? W.hw[l32 + TG_SW] : 0.0;
-        #pragma unroll 2
+        TG_PRAGMA(unroll TG_REC_UNROLL)
         for (int j = iq - 1; j >= 0; j--) {
             const double rj = __shfl_sync(TG_SMASK(), j < TG_SW ? h0 : h1, j & (TG_SW - 1), TG_SW) * W.rdi[j];
             const double *Rj = W.R + tg_rp(j);
@@ -1011,10 +1031,10 @@ TG_QFN int tg_qp_solve(const TgSqpWs &W, const double *Lsrc, int nq, int meq, do
                     double h = 0, sc = fabs(W.c[p]);
                     if (ELIM && nd > 0 && nd <= 4) {
                         const double *ar = W.Ad + (pa - meq) * W.n1;
-                        #pragma unroll 8
+                        TG_PRAGMA(unroll TG_DENSE_UNROLL)
                         for (int i = 0; i < nx; i++) { const double t = ar[i] * W.xq[i]; h += t; sc += fabs(t); }
                     } else {
-                        #pragma unroll 8
+                        TG_PRAGMA(unroll TG_DENSE_FAR_UNROLL)
                         for (int i = 0; i < nx; i++) { const double t = W.A[i * W.lda + pa] * W.xq[i]; h += t; sc += fabs(t); }
                     }
                     sv = h + W.c[p];
@@ -1411,14 +1431,14 @@ TG_QFN void tg_sqp_stage_qp(const TgLayout &L, const TgSqpWs &W)
             for (int i = lane; i < n; i += TG_NL) {
                 double h = W.g[i];
                 if (elim) {
-                    #pragma unroll 4
+                    TG_PRAGMA(unroll TG_LAG_UNROLL)
                     for (int k = 0; k < ctl.nract; k++) {
                         const int j = W.act[k];
                         h -= (tg_is_sfc_row(W, j) ? tg_sfc_entry(W, W.rotq, j, i) : W.A[i * W.lda + tg_arow(W, j)]) * W.uq[k];
                     }
                     W.v[i] = h - W.gl[i];           // (order of x; taken to QP order below)
                 } else {
-                    #pragma unroll 2
+                    TG_PRAGMA(unroll TG_LAG_FAR_UNROLL)
                     for (int k = 0; k < ctl.nract; k++) {
                         const int j = W.ract[k];
                         h -= (tg_is_sfc_row(W, j) ? tg_sfc_entry(W, W.rotq, j, i) : W.A[i * W.lda + tg_arow(W, j)]) * W.r[j];
@@ -1576,13 +1596,13 @@ TG_QFN void tg_sqp_stage_qp(const TgLayout &L, const TgSqpWs &W)
             for (int i = lane; i < n; i += TG_NL) {
                 double h = W.g[i];
                 if (elim) {
-                    #pragma unroll 4
+                    TG_PRAGMA(unroll TG_LAG_UNROLL)
                     for (int k = 0; k < ctl.nract; k++) {
                         const int j = W.act[k];
                         h -= (tg_is_sfc_row(W, j) ? tg_sfc_entry(W, W.rotq, j, i) : W.A[i * W.lda + tg_arow(W, j)]) * W.uq[k];
                     }
                 } else {
-                    #pragma unroll 2
+                    TG_PRAGMA(unroll TG_LAG_FAR_UNROLL)
                     for (int k = 0; k < ctl.nract; k++) {
                         const int j = W.ract[k];
                         h -= (tg_is_sfc_row(W, j) ? tg_sfc_entry(W, W.rotq, j, i) : W.A[i * W.lda + tg_arow(W, j)]) * W.r[j];
