@@ -2,10 +2,14 @@
 # AddressSanitizer run of the single-lane host build of the kernel source (tests/hostsim) over every fixture shape
 # (trajectory and path mode): the host buffers are sized by the same tg_sqp_workspace_doubles / tg_scratch_doubles
 # the CUDA library uses, so an out-of-bounds index of tg_eval.h / tg_sqp.h shows up here.  CPU only.
+# Two builds: the fused variant of the QP stage and the lock-step kernels' one (-DTG_FUSED_LM_FAR: the factor is updated
+# on a copy that spans J's storage, R's and the vectors behind them).
 set -e
 cd "$(dirname "$0")/.."
+for VARIANT in "" "-DTG_FUSED_LM_FAR"; do
+echo "== host build ${VARIANT:-(fused variant)}"
 g++ -std=c++14 -O1 -g -fPIC -shared -fsanitize=address -fno-omit-frame-pointer -ffp-contract=off -Wno-unknown-pragmas \
-    -DTG_WITH_SQP -o /tmp/asan_hostsim.so tests/hostsim/tg_hostsim.cpp
+    -DTG_WITH_SQP $VARIANT -o /tmp/asan_hostsim.so tests/hostsim/tg_hostsim.cpp
 LD_PRELOAD=$(g++ -print-file-name=libasan.so) ASAN_OPTIONS=detect_leaks=0 python - <<'PY'
 import sys
 sys.path[:0] = [".", "tests", "oracle"]
@@ -37,3 +41,4 @@ for name, g in helpers.load_golden("smoothing.json")["cases"].items():
     st = hs.lib.hs_smooth_solve(prob.d, prob.N, prob.k, g["resolution"], prob.scale, np.concatenate([prob.Y.flatten(), prob.b.flatten()]), x, f, nit)
     print("smooth %-26s clean (status %d, %d iterations)" % (name, st, nit[0]))
 PY
+done
