@@ -115,7 +115,8 @@ TG_HD int tg_rp(int j) { return j * (j + 1) / 2; }      // offset of column j of
 // Unroll factors of a few more loops of the stage.  Its one-warp kernels wait on instruction fetch before anything else
 // (profiles/README.md), and unrolling these loops costs more in fetches than it saves in issue slots -- measured on C4,
 // 65,536 problems: products with the active rows behind the Lagrangian gradient 4 -> 1 and the scan of the copied dense
-// rows 8 -> 1: QP stage 126 -> 110 ms.
+// rows 8 -> 1: QP stage 126 -> 110 ms; the recurrences 2 -> 1, the scan of dense rows in global memory 8 -> 2, the
+// factor copies and the product for the pin multipliers 8 -> 2: 110 -> 107 ms.
 // (the two-warp kernels do not wait on fetches -- C3 loses 2 % without the unrolling)
 #ifndef TG_LAG_UNROLL
 #define TG_LAG_UNROLL (TG_GS == 64 ? 4 : 1)
@@ -124,10 +125,10 @@ TG_HD int tg_rp(int j) { return j * (j + 1) / 2; }      // offset of column j of
 #define TG_DENSE_UNROLL (TG_GS == 64 ? 8 : 1)
 #endif
 #ifndef TG_REC_UNROLL
-#define TG_REC_UNROLL 2
+#define TG_REC_UNROLL (TG_GS == 64 ? 2 : 1)
 #endif
 #ifndef TG_DENSE_FAR_UNROLL
-#define TG_DENSE_FAR_UNROLL 8
+#define TG_DENSE_FAR_UNROLL (TG_GS == 64 ? 8 : 2)
 #endif
 #ifndef TG_LAG_FAR_UNROLL
 #define TG_LAG_FAR_UNROLL 2
@@ -523,7 +524,7 @@ TG_QFN void tg_ldl_apply_tail(int n, const double *Lm, const double *Dd, const d
     #pragma unroll 1
     for (int i = lane; i < n; i += TG_NL) {
         double h = s[i];
-        #pragma unroll 8
+        #pragma unroll 2
         for (int j = i + 1; j < n; j++) h += Lm[i * ld + j] * s[j];
         tmp[i] = Dd[i] * h;
     }
@@ -531,7 +532,7 @@ TG_QFN void tg_ldl_apply_tail(int n, const double *Lm, const double *Dd, const d
     #pragma unroll 1
     for (int i = i0 + lane; i < n; i += TG_NL) {
         double h = tmp[i];
-        #pragma unroll 8
+        #pragma unroll 2
         for (int j = 0; j < i; j++) h += Lm[j * ld + i] * tmp[j];
         out[i] = h;
     }
@@ -924,7 +925,7 @@ TG_QFN int tg_qp_solve(const TgSqpWs &W, const double *Lsrc, int nq, int meq, do
     for (int p = lane; p < nc; p += TG_NL) { W.iact[p] = 0; W.r[p] = 0; }
     const int nd = W.m - 2 * W.nsfc - meq;      // dense inequality rows
     if (ELIM && nd > 0 && nd <= 4) {
-        #pragma unroll 4
+        #pragma unroll 1
         for (int q = lane; q < nd * nx; q += TG_NL) { const int r = q / nx, i = q - r * nx; W.Ad[r * W.n1 + i] = W.A[i * W.lda + meq + r]; }
     }
     TG_SYNC();
@@ -1367,7 +1368,7 @@ TG_HD void tg_copy_doubles(double *dst, const double *src, int count, bool wide)
     if (wide && ((((size_t)dst) | ((size_t)src)) & 15) == 0) {
         double2 *d2 = reinterpret_cast<double2 *>(dst);
         const double2 *s2 = reinterpret_cast<const double2 *>(src);
-        #pragma unroll 8
+        #pragma unroll 2
         for (int q = lane; q < count / 2; q += TG_NL) d2[q] = s2[q];
         if ((count & 1) && lane == 0) dst[count - 1] = src[count - 1];
         return;
